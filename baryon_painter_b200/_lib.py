@@ -1,0 +1,244 @@
+"""ctypes binding of ``libbaryon_painter_b200.so`` (C ABI in ``include/baryon_painter_b200.h``).
+
+The library is built in-tree by ``baryon_painter_b200.build`` (``nvcc`` for sm_100a).  There is
+no fallback of any kind: if the shared object is missing or no sm_100 GPU is visible every entry
+point raises.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbaryon_painter_b200.so")
+
+BP_OK, BP_E_INVALID, BP_E_UNSUPPORTED, BP_E_CUDA, BP_E_NO_DEVICE, BP_E_NOMEM = 0, -1, -2, -3, -4, -5
+BP_CONV, BP_CONVT = 0, 1
+BP_PREC_F32, BP_PREC_BF16 = 0, 1
+BP_LATENT_GIVEN, BP_LATENT_EPS, BP_LATENT_SEED = 0, 1, 2
+BP_FLAG_TRANSFORM, BP_FLAG_INVERSE = 1, 2
+PRECISIONS = {"fp32": BP_PREC_F32, "f32": BP_PREC_F32, "float32": BP_PREC_F32,
+              "bf16": BP_PREC_BF16, "bfloat16": BP_PREC_BF16}
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+# every symbol declared in include/baryon_painter_b200.h (checked by tests/test_cabi.py)
+EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destroy", "bp_cvae_paint",
+           "bp_cvae_paint_host", "bp_cvae_read_prior", "bp_cgan_paint", "bp_cgan_paint_host",
+           "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize",
+           "bp_net_set_debug", "bp_net_read_activation", "bp_launch_count", "bp_net_flops_per_tile",
+           "bp_last_error", "bp_version")
+
+
+class LayerDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32),
+                ("kernel", ctypes.c_int32), ("stride", ctypes.c_int32), ("pad", ctypes.c_int32),
+                ("out_pad", ctypes.c_int32), ("act", ctypes.c_int32), ("act_param", ctypes.c_float),
+                ("res", ctypes.c_int32), ("weight", c_float_p), ("scale", c_float_p), ("shift", c_float_p)]
+
+
+class CvaeDesc(ctypes.Structure):
+    _fields_ = [("tile_h", ctypes.c_int32), ("tile_w", ctypes.c_int32), ("latent_h", ctypes.c_int32),
+                ("latent_w", ctypes.c_int32), ("min_z_var", ctypes.c_float),
+                ("n_prior", ctypes.c_int32), ("n_p_z_in", ctypes.c_int32), ("n_p_y_z_in", ctypes.c_int32),
+                ("n_p_mu_out", ctypes.c_int32),
+                ("prior", ctypes.POINTER(LayerDesc)), ("p_z_in", ctypes.POINTER(LayerDesc)),
+                ("p_y_z_in", ctypes.POINTER(LayerDesc)), ("p_mu_out", ctypes.POINTER(LayerDesc))]
+
+
+class TransformParams(ctypes.Structure):
+    _fields_ = [("sigma_in", c_float_p), ("sigma_out", c_float_p), ("aux", c_float_p),
+                ("k_in", ctypes.c_float), ("shift_in", ctypes.c_float),
+                ("k_out", ctypes.c_float), ("shift_out", ctypes.c_float)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "baryon_painter_b200: %s is missing -- build it with `python -m baryon_painter_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for the paint path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, u64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_float
+    lib.bp_device_count.restype = i32
+    lib.bp_version.restype = i32
+    lib.bp_last_error.restype = ctypes.c_char_p
+    lib.bp_launch_count.restype = ctypes.c_int64
+    lib.bp_launch_count.argtypes = [i32]
+    lib.bp_net_flops_per_tile.restype = ctypes.c_double
+    lib.bp_net_flops_per_tile.argtypes = [vp]
+    lib.bp_cvae_create.argtypes = [ctypes.POINTER(CvaeDesc), i32, i32, i32, ctypes.POINTER(vp)]
+    lib.bp_cgan_create.argtypes = [ctypes.POINTER(LayerDesc), i32, i32, i32, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.bp_net_destroy.argtypes = [vp]
+    lib.bp_net_destroy.restype = None
+    tpp = ctypes.POINTER(TransformParams)
+    lib.bp_cvae_paint.argtypes = [vp, vp, vp, i32, u64, tpp, i32, vp, i32, vp]
+    lib.bp_cvae_paint_host.argtypes = [vp, vp, vp, i32, u64, tpp, i32, vp, i32]
+    lib.bp_cvae_read_prior.argtypes = [vp, vp, vp, i32]
+    lib.bp_cgan_paint.argtypes = [vp, vp, tpp, i32, vp, i32, vp]
+    lib.bp_cgan_paint_host.argtypes = [vp, vp, tpp, i32, vp, i32]
+    lib.bp_cvae_paint_variance_host.argtypes = [vp, vp, tpp, i32, u64, vp, vp, i32]
+    lib.bp_stitch_accumulate.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, f32, vp]
+    lib.bp_stitch_finalize.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
+    lib.bp_net_set_debug.argtypes = [vp, i32]
+    lib.bp_net_read_activation.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    """Map a BP_E_* status to the exception the reference raises in the same situation."""
+    if rc == BP_OK:
+        return
+    msg = load().bp_last_error().decode("utf-8", "replace")
+    if rc == BP_E_INVALID:
+        raise ValueError(msg)
+    if rc == BP_E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == BP_E_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def _fptr(a):
+    return a.ctypes.data_as(c_float_p) if a is not None else c_float_p()
+
+
+def make_layer_descs(folded):
+    """[arch.FoldedLayer] -> (ctypes array of LayerDesc, keep-alive list of numpy arrays)."""
+    from . import arch
+    arr = (LayerDesc * max(len(folded), 1))()
+    keep = []
+    for i, f in enumerate(folded):
+        s = f.spec
+        w = np.ascontiguousarray(f.weight, np.float32)
+        sc = np.ascontiguousarray(f.scale, np.float32)
+        sh = np.ascontiguousarray(f.shift, np.float32)
+        keep += [w, sc, sh]
+        arr[i] = LayerDesc(BP_CONV if s.kind == "conv" else BP_CONVT, s.cin, s.cout, s.k, s.stride, s.pad,
+                           s.out_pad, arch.ACT_IDS[s.act], float(f.act_param), int(s.res),
+                           _fptr(w), _fptr(sc), _fptr(sh))
+    return arr, keep
+
+
+class Net:
+    """Owner of one ``bp_net*``."""
+
+    def __init__(self, handle, kind, tile_hw, latent_hw, precision, max_batch, device):
+        self.handle, self.kind = handle, kind
+        self.tile_hw, self.latent_hw = tuple(tile_hw), tuple(latent_hw) if latent_hw else None
+        self.precision, self.max_batch, self.device = precision, max_batch, device
+
+    @classmethod
+    def create_cvae(cls, stacks, tile_hw, latent_hw, min_z_var, precision, max_batch, device):
+        lib = load()
+        keep, arrs = [], {}
+        for name in ("prior_network", "p_z_in", "p_y_z_in", "p_mu_out"):
+            arrs[name], k = make_layer_descs(stacks.get(name, []))
+            keep += k
+        d = CvaeDesc(tile_hw[0], tile_hw[1], latent_hw[0], latent_hw[1], float(min_z_var),
+                     len(stacks.get("prior_network", [])), len(stacks["p_z_in"]), len(stacks["p_y_z_in"]),
+                     len(stacks["p_mu_out"]), arrs["prior_network"], arrs["p_z_in"], arrs["p_y_z_in"],
+                     arrs["p_mu_out"])
+        h = ctypes.c_void_p()
+        check(lib.bp_cvae_create(ctypes.byref(d), PRECISIONS[precision], int(max_batch), int(device),
+                                 ctypes.byref(h)))
+        return cls(h, "cvae", tile_hw, latent_hw, precision, max_batch, device)
+
+    @classmethod
+    def create_cgan(cls, layers, tile_hw, precision, max_batch, device):
+        lib = load()
+        arr, keep = make_layer_descs(layers)
+        h = ctypes.c_void_p()
+        check(lib.bp_cgan_create(arr, len(layers), tile_hw[0], tile_hw[1], PRECISIONS[precision], int(max_batch),
+                                 int(device), ctypes.byref(h)))
+        return cls(h, "cgan", tile_hw, None, precision, max_batch, device)
+
+    def close(self):
+        if self.handle:
+            load().bp_net_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def flops_per_tile(self):
+        return load().bp_net_flops_per_tile(self.handle)
+
+    # -- helpers -------------------------------------------------------------------------
+    @staticmethod
+    def _tp(sigma_in, sigma_out, aux, k_in, shift_in, k_out, shift_out):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        sigma_in, sigma_out, aux = f(sigma_in), f(sigma_out), f(aux)
+        tp = TransformParams(_fptr(sigma_in), _fptr(sigma_out), _fptr(aux), k_in, shift_in, k_out, shift_out)
+        return tp, (sigma_in, sigma_out, aux)
+
+    def cvae_paint_host(self, tiles, latent, mode, seed, tparams, flags):
+        """tiles float32 [n,H,W] (host) -> float32 [n,H,W]."""
+        lib = load()
+        n = tiles.shape[0]
+        tiles = np.ascontiguousarray(tiles, np.float32)
+        out = np.empty((n, *self.tile_hw), np.float32)
+        lat = None if latent is None else np.ascontiguousarray(latent, np.float32)
+        tp, keep = self._tp(*tparams)
+        check(lib.bp_cvae_paint_host(self.handle, tiles.ctypes.data, lat.ctypes.data if lat is not None else None,
+                                     mode, ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.byref(tp), flags,
+                                     out.ctypes.data, n))
+        return out
+
+    def cvae_paint_device(self, tiles_ptr, latent_ptr, mode, seed, tparams, flags, out_ptr, n, stream=0):
+        tp, keep = self._tp(*tparams)
+        check(load().bp_cvae_paint(self.handle, tiles_ptr, latent_ptr, mode, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                   ctypes.byref(tp), flags, out_ptr, n, stream))
+
+    def cvae_read_prior(self, n):
+        mu = np.empty((n, *self.latent_hw), np.float32)
+        lv = np.empty((n, *self.latent_hw), np.float32)
+        check(load().bp_cvae_read_prior(self.handle, mu.ctypes.data, lv.ctypes.data, n))
+        return mu, lv
+
+    def cvae_paint_variance_host(self, tiles, tparams, n_draws, seed):
+        n = tiles.shape[0]
+        tiles = np.ascontiguousarray(tiles, np.float32)
+        mean = np.empty((n, *self.tile_hw), np.float32)
+        var = np.empty((n, *self.tile_hw), np.float32)
+        tp, keep = self._tp(*tparams)
+        check(load().bp_cvae_paint_variance_host(self.handle, tiles.ctypes.data, ctypes.byref(tp), int(n_draws),
+                                                 ctypes.c_uint64(seed & (2 ** 64 - 1)), mean.ctypes.data,
+                                                 var.ctypes.data, n))
+        return mean, var
+
+    def cgan_paint_host(self, tiles, tparams, flags):
+        n = tiles.shape[0]
+        tiles = np.ascontiguousarray(tiles, np.float32)
+        out = np.empty((n, *self.tile_hw), np.float32)
+        tp, keep = self._tp(*tparams)
+        check(load().bp_cgan_paint_host(self.handle, tiles.ctypes.data, ctypes.byref(tp), flags, out.ctypes.data, n))
+        return out
+
+    def cgan_paint_device(self, tiles_ptr, tparams, flags, out_ptr, n, stream=0):
+        tp, keep = self._tp(*tparams)
+        check(load().bp_cgan_paint(self.handle, tiles_ptr, ctypes.byref(tp), flags, out_ptr, n, stream))
+
+    def set_debug(self, on):
+        check(load().bp_net_set_debug(self.handle, int(bool(on))))
+
+    def read_activation(self, stack, layer, shape):
+        out = np.empty(shape, np.float32)
+        check(load().bp_net_read_activation(self.handle, stack, layer, out.ctypes.data, out.size))
+        return out
+
+
+def launch_count(reset=False):
+    return int(load().bp_launch_count(int(bool(reset))))

@@ -1,0 +1,191 @@
+"""GPU parity of the CVAE paint path (through the C ABI) against the committed golden vectors
+(generated from the unmodified reference by oracle/make_golden.py) and against the oracle
+restatement on fresh seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 path <= 1e-4 relative L2 per tile; bf16 path <= 1e-2
+relative L2 per tile and auto/cross power spectra within 1 %.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+# layer-boundary tensors: fp32 accumulates ~1e-6 per layer; bf16 ~ 3e-3 per layer
+TOL_LAYER = {"fp32": 2e-5, "bf16": 2e-2}
+
+
+def _painter(tile, seed, precision, max_batch=8):
+    from baryon_painter_b200.painter import CVAEPainter
+    return CVAEPainter.synthetic(tile_size=tile, seed=seed, precision=precision, max_batch=max_batch)
+
+
+def _tiles(g, n):
+    from baryon_painter_b200 import synthetic
+    return synthetic.synthetic_dm_tiles(n, int(g["tile_size"]), seed0=int(g["tiles_seed0"]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_layer_boundaries_t64(precision):
+    from baryon_painter_b200 import arch
+    g = np.load(os.path.join(GOLDEN, "cvae_t64_layers.npz"))
+    p = _painter(64, int(g["seed"]), precision)
+    p.model.net.set_debug(True)
+    tiles = _tiles(g, 1)
+    out = p.paint(tiles[0], z=float(g["z"][0]), eps=g["eps"][0])
+    assert rel_l2(out, g["painted_E"][0]) <= TOL[precision]
+    stack_ids = {"prior_network": 0, "p_z_in": 1, "p_y_z_in": 2, "p_mu_out": 3}
+    worst = 0.0
+    for name, sid in stack_ids.items():
+        specs = p.model.stacks[name]
+        # golden taps are keyed by the Sequential index of the last module of each conv group
+        keys = sorted((k for k in g.files if k.startswith("tap:" + name + ".")), key=lambda s: int(s.split(".")[-1]))
+        # residual blocks contribute one tap (after the block) for two convolutions
+        li = -1
+        for k in keys:
+            li += 1
+            while specs[li].res == arch.RES_OPEN:
+                li += 1
+            s = specs[li]
+            ref = g[k]
+            got = p.model.net.read_activation(sid, li, (1, *ref.shape))[0]
+            e = rel_l2(got, ref)
+            worst = max(worst, e)
+            assert e <= TOL_LAYER[precision], (k, li, e)
+    mu, lv = p.model.net.cvae_read_prior(1)
+    assert rel_l2(mu[0], g["z_mu"][0][0]) <= TOL_LAYER[precision]
+    assert rel_l2(lv[0], g["z_log_var"][0][0]) <= TOL_LAYER[precision] or np.abs(g["z_log_var"]).max() < 1e-6
+    print("worst layer rel-L2", precision, worst)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_golden_t128(precision):
+    g = np.load(os.path.join(GOLDEN, "cvae_t128.npz"))
+    p = _painter(128, int(g["seed"]), precision)
+    tiles = _tiles(g, 4)
+    zs = g["z"]
+    # batched, both latent modes
+    out_e = p.paint_batch(tiles, z=zs, eps=g["eps"])
+    out_l = p.paint_batch(tiles, z=zs, latents=g["eps"])
+    for i in range(4):
+        assert rel_l2(out_e[i], g["painted_E"][i]) <= TOL[precision], ("E", i)
+        assert rel_l2(out_l[i], g["painted_L"][i]) <= TOL[precision], ("L", i)
+    # one tile at a time through paint(), the reference entry point
+    for i in range(4):
+        o = p.paint(tiles[i], z=float(zs[i]), eps=g["eps"][i])
+        assert o.shape == (128, 128) and o.dtype == np.float32
+        assert rel_l2(o, g["painted_E"][i]) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_golden_t512(precision):
+    g = np.load(os.path.join(GOLDEN, "cvae_t512.npz"))
+    p = _painter(512, int(g["seed"]), precision)
+    tiles = _tiles(g, 2)
+    o_e = p.paint(tiles[0], z=float(g["z"][0]), eps=g["eps"][0])
+    o_l = p.paint(tiles[1], z=float(g["z"][1]), latent=g["eps"][1])
+    assert rel_l2(o_e, g["painted_E"][0]) <= TOL[precision]
+    assert rel_l2(o_l, g["painted_L"][0]) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vs_oracle_fresh_inputs(precision):
+    """same seeded weights/tiles/latents through the oracle (CPU) and the CUDA path; ragged batch
+    (5 tiles with chunking) and redshifts outside the stats table (clamped)."""
+    import torch
+    from oracle.cvae_oracle import CVAEOracle, pseudo_Pofk
+    from baryon_painter_b200 import arch, synthetic, transforms
+    torch.set_num_threads(os.cpu_count())
+    tile = 128
+    A = arch.fiducial_cvae_architecture(tile)
+    sd = synthetic.synthetic_cvae_state_dict(A, seed=11)
+    stats = transforms.fiducial_stats()
+    orc = CVAEOracle(A, sd)
+    p = _painter(tile, 11, precision, max_batch=3)          # forces 2 host batches for 5 tiles
+    tiles = synthetic.synthetic_dm_tiles(5, tile, seed0=500)
+    zs = np.array([-0.1, 0.06, 0.5, 1.9, 3.0])
+    eps = synthetic.synthetic_latents(5, (tile // 32, tile // 32), seed=9)
+    ref = orc.paint_batch(tiles, zs, stats, eps=eps)
+    out = p.paint_batch(tiles, z=zs, eps=eps)
+    for i in range(5):
+        assert rel_l2(out[i], ref[i]) <= TOL[precision], i
+    # power spectra (north_star: within 1 % for the bf16 path)
+    for i in range(5):
+        k, pa_ref = pseudo_Pofk(ref[i], ref[i])
+        _, pa = pseudo_Pofk(out[i], out[i])
+        _, px_ref = pseudo_Pofk(tiles[i], ref[i])
+        _, px = pseudo_Pofk(tiles[i], out[i])
+        assert np.max(np.abs(pa / pa_ref - 1)) <= 0.01
+        big = np.abs(px_ref) > 1e-3 * np.abs(px_ref).max()
+        assert np.max(np.abs(px[big] / px_ref[big] - 1)) <= 0.01
+
+
+def test_api_semantics():
+    p = _painter(64, 3, "fp32")
+    from baryon_painter_b200 import synthetic
+    t = synthetic.synthetic_dm_tiles(1, 64, seed0=1)[0]
+    with pytest.raises(ValueError, match="Shape mismatch between input and model"):
+        p.paint(np.ones((32, 32), np.float32), z=0.0)
+    with pytest.raises(ValueError, match="Shape mismatch between input and model"):
+        p.paint(t, z=0.0, transform=False)                 # reference: (H,W) without atleast_3d fails
+    eps = np.zeros((1, 2, 2), np.float32)
+    full = p.paint(t, z=0.3, eps=eps)
+    assert full.shape == (64, 64) and full.dtype == np.float32
+    # transform=False takes the transformed (1,H,W) input; inverse_transform=False returns (1,1,H,W)
+    y = p.transform(t, field="dm", z=0.3)
+    assert y.shape == (1, 64, 64) and y.dtype == np.float32
+    raw = p.paint(y, z=0.3, transform=False, inverse_transform=False, eps=eps)
+    assert raw.shape == (1, 1, 64, 64)
+    back = p.inverse_transform(raw, field="pressure", z=0.3)
+    assert rel_l2(back, full) <= 1e-5
+    # input is not mutated, output is a fresh array
+    t0 = t.copy()
+    a = p.paint(t, z=0.0, eps=eps)
+    b = p.paint(t, z=0.0, eps=eps)
+    assert np.array_equal(t, t0) and a is not b and np.array_equal(a, b)
+    # unseeded paint draws a latent on the device: two calls differ, same seed agrees
+    c = p.paint(t, z=0.0)
+    d = p.paint(t, z=0.0)
+    assert not np.array_equal(c, d)
+    assert np.array_equal(p.paint(t, z=0.0, seed=5), p.paint(t, z=0.0, seed=5))
+    # empty batch
+    assert p.paint_batch(np.zeros((0, 64, 64), np.float32), z=0.0).shape == (0, 64, 64)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """save_state_to_file / load_state_from_file keep the (model_state, model_meta) contract."""
+    import torch
+    from baryon_painter_b200.painter import CVAEPainter
+    p = _painter(64, 3, "fp32")
+    files = (str(tmp_path / "model_state"), str(tmp_path / "model_meta"))
+    p.save_state_to_file(files)
+    sd = torch.load(files[0])
+    assert len(sd) == 179
+    q = CVAEPainter(files, precision="fp32")
+    for k in ("L", "n_grid", "tile_L", "n_tile", "tile_size", "input_field", "label_fields", "scale_to_SLICS"):
+        assert getattr(q, k) == getattr(p, k)
+    from baryon_painter_b200 import synthetic
+    t = synthetic.synthetic_dm_tiles(1, 64, seed0=4)[0]
+    eps = np.ones((1, 2, 2), np.float32)
+    assert np.array_equal(p.paint(t, z=0.7, eps=eps), q.paint(t, z=0.7, eps=eps))
+    with pytest.raises(ValueError):
+        q.load_state_from_file("model_state")
+    bad = dict(sd)
+    bad.pop("p_mu_out.0.weight")
+    with pytest.raises(RuntimeError, match="Missing key"):
+        q.model.load_state_dict(bad)
+
+
+def test_variance_maps():
+    p = _painter(64, 3, "fp32")
+    from baryon_painter_b200 import synthetic
+    tiles = synthetic.synthetic_dm_tiles(3, 64, seed0=8)
+    mean, var = p.paint_variance(tiles, z=[0.0, 0.5, 1.0], n_draws=16, seed=2)
+    assert mean.shape == var.shape == (3, 64, 64)
+    assert np.all(np.isfinite(mean)) and np.all(var >= 0) and var.max() > 0
+    mean2, var2 = p.paint_variance(tiles, z=[0.0, 0.5, 1.0], n_draws=16, seed=2)
+    assert np.array_equal(mean, mean2) and np.array_equal(var, var2)
