@@ -15,11 +15,12 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbaryon_painter_b200.so")
 
 BP_OK, BP_E_INVALID, BP_E_UNSUPPORTED, BP_E_CUDA, BP_E_NO_DEVICE, BP_E_NOMEM = 0, -1, -2, -3, -4, -5
 BP_CONV, BP_CONVT = 0, 1
-BP_PREC_F32, BP_PREC_BF16 = 0, 1
+BP_PREC_F32, BP_PREC_BF16, BP_PREC_F16 = 0, 1, 2
 BP_LATENT_GIVEN, BP_LATENT_EPS, BP_LATENT_SEED = 0, 1, 2
 BP_FLAG_TRANSFORM, BP_FLAG_INVERSE = 1, 2
 PRECISIONS = {"fp32": BP_PREC_F32, "f32": BP_PREC_F32, "float32": BP_PREC_F32,
-              "bf16": BP_PREC_BF16, "bfloat16": BP_PREC_BF16}
+              "bf16": BP_PREC_BF16, "bfloat16": BP_PREC_BF16,
+              "fp16": BP_PREC_F16, "f16": BP_PREC_F16, "float16": BP_PREC_F16}
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 
@@ -27,7 +28,8 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destroy", "bp_cvae_paint",
            "bp_cvae_paint_host", "bp_cvae_read_prior", "bp_cgan_paint", "bp_cgan_paint_host",
            "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize",
-           "bp_net_set_debug", "bp_net_read_activation", "bp_launch_count", "bp_net_flops_per_tile",
+           "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
+           "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile",
            "bp_last_error", "bp_version")
 
 
@@ -89,6 +91,9 @@ def load():
     lib.bp_stitch_finalize.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
     lib.bp_net_set_debug.argtypes = [vp, i32]
     lib.bp_net_read_activation.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
+    lib.bp_net_set_profile.argtypes = [vp, i32]
+    lib.bp_net_read_profile.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
+    lib.bp_net_layer_info.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
     _lib = lib
     return lib
 
@@ -233,6 +238,23 @@ class Net:
 
     def set_debug(self, on):
         check(load().bp_net_set_debug(self.handle, int(bool(on))))
+
+    def set_profile(self, on):
+        check(load().bp_net_set_profile(self.handle, int(bool(on))))
+
+    def layer_info(self, stack, layer):
+        fl = ctypes.c_double()
+        geom = (ctypes.c_int * 10)()
+        check(load().bp_net_layer_info(self.handle, stack, layer, ctypes.byref(fl), geom))
+        keys = ("kind", "cin", "cout", "kernel", "stride", "H", "W", "OH", "OW", "tensor")
+        d = dict(zip(keys, list(geom)))
+        d["flops"] = fl.value
+        return d
+
+    def read_profile(self, stack, layer):
+        ms, cnt = ctypes.c_double(), ctypes.c_int()
+        check(load().bp_net_read_profile(self.handle, stack, layer, ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, cnt.value
 
     def read_activation(self, stack, layer, shape):
         out = np.empty(shape, np.float32)

@@ -91,8 +91,9 @@ struct Layer {
   float* wmat = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
-  // bf16 tensor-core path (filled by bp_bf16.cu when the layer qualifies)
+  // 16-bit tensor-core path (filled by bp_tc.cu when the layer qualifies)
   void* tc = nullptr;
+  std::vector<float> host_weight;  // PyTorch-layout copy kept for the tensor-core packing
   double flops = 0;             // 2*MACs per sample (SURVEY App. A counting)
 };
 

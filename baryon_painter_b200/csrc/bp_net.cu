@@ -12,7 +12,7 @@
 #include <new>
 
 #include "bp_common.h"
-#include "bp_bf16.h"
+#include "bp_tc.h"
 
 namespace bp {
 
@@ -47,6 +47,8 @@ int pack_layer(const bp_layer_desc& d, int H, int W, Layer* out) {
   BP_REQUIRE(d.cin > 0 && d.cout > 0 && d.kernel > 0 && d.stride > 0 && d.pad >= 0 && d.out_pad >= 0,
              BP_E_INVALID, "bad convolution geometry");
   BP_REQUIRE(d.weight != nullptr, BP_E_INVALID, "layer without weights");
+  l.host_weight.assign(d.weight, d.weight + (size_t)d.cin * d.cout * d.kernel * d.kernel);
+  l.d.weight = nullptr; l.d.scale = nullptr; l.d.shift = nullptr;
   const int k = d.kernel, s = d.stride, p = d.pad;
   std::vector<int4> ktab;
   std::vector<float> wmat;
@@ -120,7 +122,7 @@ int pack_layer(const bp_layer_desc& d, int H, int W, Layer* out) {
 
 void free_layer(Layer* l) {
   cudaFree(l->ktab); cudaFree(l->wmat); cudaFree(l->scale); cudaFree(l->shift);
-  bf16_free_layer(l);
+  tc_free_layer(l);
   l->ktab = nullptr; l->wmat = nullptr; l->scale = nullptr; l->shift = nullptr;
 }
 
@@ -148,7 +150,7 @@ struct bp_net {
   Stack st[4];
   int nstacks = 0;
   float* in_cat = nullptr;
-  float* pool[3] = {nullptr, nullptr, nullptr};
+  float* pool[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t pool_floats = 0;
   float* latent = nullptr;
   float* prior_all = nullptr;
@@ -164,7 +166,9 @@ struct bp_net {
   bool debug = false;
   std::vector<float*> dbg[4];
   int dbg_n = 0;
-  void* bf16 = nullptr;  // bf16 workspace (bp_bf16.cu)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per recorded layer launch
+  std::vector<int> prof_ids;                                     // stack*1000 + layer
   double flops_per_tile = 0;
 };
 
@@ -203,9 +207,8 @@ static void destroy_net(bp_net* net) {
     for (auto& l : net->st[s].layers) free_layer(&l);
     for (float* p : net->dbg[s]) cudaFree(p);
   }
-  bf16_free_net(net->bf16);
   cudaFree(net->in_cat);
-  for (int i = 0; i < 3; ++i) cudaFree(net->pool[i]);
+  for (int i = 0; i < 4; ++i) cudaFree(net->pool[i]);
   cudaFree(net->latent); cudaFree(net->prior_all); cudaFree(net->prior_keep); cudaFree(net->params);
   cudaFree(net->d_in); cudaFree(net->d_out); cudaFree(net->d_lat);
   cudaFree(net->var_mean); cudaFree(net->var_m2);
@@ -245,12 +248,12 @@ static int finish_create(bp_net* net) {
   }
   // chunk: keep the three rotating activation buffers of one chunk around L2 size (126 MB) so that
   // a layer's output is still cache-resident when the next layer reads it
-  int chunk = net->prec == BP_PREC_BF16 ? 8 : 4;
+  int chunk = net->prec == BP_PREC_F32 ? 4 : 8;
   if (const char* e = getenv("BP_CHUNK")) chunk = std::max(1, atoi(e));
   net->chunk = std::min(chunk, net->max_batch);
   net->pool_floats = mx * net->chunk;
   BP_CUDA_TRY(cudaMalloc(&net->in_cat, sizeof(float) * net->in_c * HW * net->chunk));
-  for (int i = 0; i < 3; ++i) BP_CUDA_TRY(cudaMalloc(&net->pool[i], sizeof(float) * net->pool_floats));
+  for (int i = 0; i < 4; ++i) BP_CUDA_TRY(cudaMalloc(&net->pool[i], sizeof(float) * net->pool_floats));
   const size_t lhw = (size_t)net->lh * net->lw;
   if (net->kind == NET_CVAE) {
     BP_CUDA_TRY(cudaMalloc(&net->latent, sizeof(float) * lhw * net->chunk));
@@ -270,11 +273,34 @@ static int finish_create(bp_net* net) {
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_in[i], cudaEventDisableTiming));
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_done[i], cudaEventDisableTiming));
   }
-  if (net->prec == BP_PREC_BF16) {
-    std::vector<std::vector<Layer>*> stacks;
-    for (int s = 0; s < net->nstacks; ++s) stacks.push_back(&net->st[s].layers);
-    int rc = bf16_prepare_net(stacks, net->chunk, &net->bf16);
-    if (rc != BP_OK) return rc;
+  if (net->prec != BP_PREC_F32) {
+    const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
+    // sequences that stay in the 16-bit c8 layout: the prior network; p_z_in; p_y_z_in + p_mu_out
+    // (CGAN: the generator).  A layer runs on the tensor cores when tc_layer_eligible() says so.
+    for (int s = 0; s < net->nstacks; ++s) {
+      const bool continues = net->kind == NET_CVAE && s == ST_MU;   // p_mu_out continues p_y_z_in
+      std::vector<Layer>& L = net->st[s].layers;
+      for (size_t i = 0; i < L.size(); ++i) {
+        const bool first = (i == 0) && !continues;
+        if (!tc_layer_eligible(L[i].d, first)) continue;
+        if (!first) {
+          // the producer of this layer's input must be a tensor-core layer too, unless we repack
+          const Layer* prev = i > 0 ? &L[i - 1] : &net->st[ST_PYZ].layers.back();
+          if (!prev->tc && (L[i].d.cin % 8) != 0) continue;
+        }
+        int rc = tc_pack_layer(&L[i], fmt);
+        if (rc != BP_OK) return rc;
+      }
+      // a residual block runs on one path only
+      for (size_t i = 0; i < L.size(); ++i)
+        if (L[i].d.res == BP_RES_OPEN) {
+          size_t j = i;
+          while (L[j].d.res != BP_RES_CLOSE) ++j;
+          bool all = true;
+          for (size_t q = i; q <= j; ++q) all = all && L[q].tc;
+          if (!all) for (size_t q = i; q <= j; ++q) tc_free_layer(&L[q]);
+        }
+    }
   }
   return BP_OK;
 }
@@ -288,62 +314,119 @@ struct PostOp {
   float k = 0.f, shift = 0.f;
 };
 
-static float* pick_buffer(bp_net* net, const float* a, const float* b) {
-  for (int i = 0; i < 3; ++i)
-    if (net->pool[i] != a && net->pool[i] != b) return net->pool[i];
+static float* pick_buffer(bp_net* net, const void* a, const void* b, const void* c = nullptr) {
+  for (int i = 0; i < 4; ++i)
+    if (net->pool[i] != a && net->pool[i] != b && net->pool[i] != c) return net->pool[i];
   return nullptr;
 }
 
-// run one sub-network on nb samples.  `in` has per-sample stride in_bs; the last layer writes to
-// final_out (stride final_bs) when given, else to a pool buffer which is returned in *result.
-static int run_stack(bp_net* net, int sidx, const float* in, long long in_bs, float* final_out,
-                     long long final_bs, const PostOp& post, int nb, cudaStream_t s, float** result) {
+// an activation tensor: fp32 NCHW with per-sample stride `bs`, or the 16-bit c8 layout of the
+// tensor-core path ([nb][C/8][H][W][8], dense)
+struct ActRef {
+  const void* ptr = nullptr;
+  long long bs = 0;
+  bool c8 = false;
+};
+
+static int record_debug(bp_net* net, int sidx, int i, int nl, const Layer& l, const void* out, long long out_bs,
+                        bool c8, int nb, cudaStream_t s) {
+  const size_t per = (size_t)l.d.cout * l.OHF * l.OWF;
+  if (net->dbg[sidx].size() < (size_t)nl) net->dbg[sidx].resize(nl, nullptr);
+  if (!net->dbg[sidx][i]) BP_CUDA_TRY(cudaMalloc(&net->dbg[sidx][i], sizeof(float) * per * net->chunk));
+  if (c8)
+    return launch_unpack_c8(out, l.d.cout, l.OHF * l.OWF, net->dbg[sidx][i], (long long)per, nb,
+                            net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16, s);
+  BP_CUDA_TRY(cudaMemcpy2DAsync(net->dbg[sidx][i], per * sizeof(float), out, out_bs * sizeof(float),
+                                per * sizeof(float), nb, cudaMemcpyDeviceToDevice, s));
+  return BP_OK;
+}
+
+// run one sub-network on nb samples.  The last layer writes fp32 NCHW to final_out (stride final_bs)
+// when given; otherwise to a pool buffer returned in *result (c8 if `c8_result_ok` and the last layer
+// runs on the tensor cores).
+static int run_stack(bp_net* net, int sidx, ActRef in, float* final_out, long long final_bs, const PostOp& post,
+                     int nb, cudaStream_t s, ActRef* result, bool c8_result_ok = false) {
   Stack& st = net->st[sidx];
-  const float* cur = in;
-  long long cur_bs = in_bs;
-  const float* cur_base = in;  // pool buffer identity of `cur` (for allocation)
-  const float* skip = nullptr;
-  long long skip_bs = 0;
+  ActRef cur = in;
+  ActRef skip;
   const int nl = (int)st.layers.size();
-  if (net->prec == BP_PREC_BF16) {
-    int rc = bf16_run_stack(net->bf16, sidx, st.layers, cur, cur_bs, final_out, final_bs, post.post, post.sigma,
-                            post.k, post.shift, nb, s, result, net->pool, net->debug ? &net->dbg[sidx] : nullptr,
-                            net->chunk);
-    return rc;
-  }
+  const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
   for (int i = 0; i < nl; ++i) {
     Layer& l = st.layers[i];
     const bool last = (i == nl - 1);
-    if (l.d.res == BP_RES_OPEN) { skip = cur; skip_bs = cur_bs; }
-    float* out;
-    long long out_bs;
+    const bool use_tc = l.tc != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (net->profile) {
+      BP_CUDA_TRY(cudaEventCreate(&e0)); BP_CUDA_TRY(cudaEventCreate(&e1));
+      BP_CUDA_TRY(cudaEventRecord(e0, s));
+    }
+    // ---- bring the input into the representation this layer's kernel reads
+    if (use_tc && !cur.c8) {
+      float* pk = pick_buffer(net, cur.ptr, skip.ptr);
+      BP_REQUIRE(pk, BP_E_INVALID, "internal: no free activation buffer");
+      int rc = launch_pack_c8(static_cast<const float*>(cur.ptr), cur.bs, l.d.cin, l.H * l.W, pk, nb, fmt, s);
+      if (rc != BP_OK) return rc;
+      cur.ptr = pk; cur.bs = 0; cur.c8 = true;
+    } else if (!use_tc && cur.c8) {
+      float* up = pick_buffer(net, cur.ptr, skip.ptr);
+      BP_REQUIRE(up, BP_E_INVALID, "internal: no free activation buffer");
+      const long long bs = (long long)l.d.cin * l.H * l.W;
+      int rc = launch_unpack_c8(cur.ptr, l.d.cin, l.H * l.W, up, bs, nb, fmt, s);
+      if (rc != BP_OK) return rc;
+      cur.ptr = up; cur.bs = bs; cur.c8 = false;
+    }
+    if (l.d.res == BP_RES_OPEN) skip = cur;
+    // ---- where the output goes
+    const long long dense_bs = (long long)l.d.cout * l.OHF * l.OWF;
+    ActRef out;
     if (last && final_out) {
-      out = final_out; out_bs = final_bs;
+      out.ptr = final_out; out.bs = final_bs; out.c8 = false;
     } else {
-      out = pick_buffer(net, cur_base, skip);
-      BP_REQUIRE(out != nullptr, BP_E_INVALID, "internal: no free activation buffer");
-      out_bs = (long long)l.d.cout * l.OHF * l.OWF;
+      const bool next_tc = last ? c8_result_ok : (st.layers[i + 1].tc != nullptr);
+      out.ptr = pick_buffer(net, cur.ptr, skip.ptr, in.ptr);
+      BP_REQUIRE(out.ptr, BP_E_INVALID, "internal: no free activation buffer");
+      out.c8 = use_tc && next_tc;
+      out.bs = out.c8 ? 0 : dense_bs;
     }
-    ConvArgs a;
-    memset(&a, 0, sizeof(a));
-    a.in = cur; a.in_bs = cur_bs; a.out = out; a.out_bs = out_bs; a.nb = nb;
-    if (l.d.res == BP_RES_CLOSE) { a.skip = skip; a.skip_bs = skip_bs; }
-    if (last && post.post != POST_NONE) {
-      a.post = post.post; a.post_sigma = post.sigma; a.post_k = post.k; a.post_shift = post.shift;
+    int rc;
+    if (use_tc) {
+      BP_REQUIRE(!(last && post.post != POST_NONE), BP_E_UNSUPPORTED,
+                 "inverse transform fused into a tensor-core layer is not implemented");
+      const void* sk = nullptr;
+      if (l.d.res == BP_RES_CLOSE) {
+        BP_REQUIRE(skip.c8, BP_E_INVALID, "internal: residual skip is not in the c8 layout");
+        sk = skip.ptr;
+      }
+      rc = launch_conv_tc(l, cur.ptr, out.c8 ? const_cast<void*>(out.ptr) : nullptr,
+                          out.c8 ? nullptr : static_cast<float*>(const_cast<void*>(out.ptr)), out.bs, sk, nb, s);
+    } else {
+      ConvArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in = static_cast<const float*>(cur.ptr); a.in_bs = cur.bs;
+      a.out = static_cast<float*>(const_cast<void*>(out.ptr)); a.out_bs = out.bs; a.nb = nb;
+      if (l.d.res == BP_RES_CLOSE) {
+        BP_REQUIRE(!skip.c8, BP_E_INVALID, "internal: residual skip is not fp32");
+        a.skip = static_cast<const float*>(skip.ptr); a.skip_bs = skip.bs;
+      }
+      if (last && post.post != POST_NONE) {
+        a.post = post.post; a.post_sigma = post.sigma; a.post_k = post.k; a.post_shift = post.shift;
+      }
+      rc = launch_conv_f32(l, a, s);
     }
-    int rc = launch_conv_f32(l, a, s);
     if (rc != BP_OK) return rc;
-    if (l.d.res == BP_RES_CLOSE) skip = nullptr;
-    if (net->debug) {
-      const size_t per = (size_t)l.d.cout * l.OHF * l.OWF;
-      if (net->dbg[sidx].size() < (size_t)nl) net->dbg[sidx].resize(nl, nullptr);
-      if (!net->dbg[sidx][i]) BP_CUDA_TRY(cudaMalloc(&net->dbg[sidx][i], sizeof(float) * per * net->chunk));
-      BP_CUDA_TRY(cudaMemcpy2DAsync(net->dbg[sidx][i], per * sizeof(float), out, out_bs * sizeof(float),
-                                    per * sizeof(float), nb, cudaMemcpyDeviceToDevice, s));
+    if (net->profile) {
+      BP_CUDA_TRY(cudaEventRecord(e1, s));
+      net->prof_events.emplace_back(e0, e1);
+      net->prof_ids.push_back(sidx * 1000 + i);
     }
-    cur = out; cur_bs = out_bs; cur_base = out;
+    if (l.d.res == BP_RES_CLOSE) skip = ActRef();
+    if (net->debug) {
+      rc = record_debug(net, sidx, i, nl, l, out.ptr, out.bs, out.c8, nb, s);
+      if (rc != BP_OK) return rc;
+    }
+    cur = out;
   }
-  if (result) *result = const_cast<float*>(cur);
+  if (result) *result = cur;
   return BP_OK;
 }
 
@@ -363,6 +446,7 @@ static int upload_params(bp_net* net, const bp_transform_params* tp, int flags, 
 // stage A of one CVAE chunk: forward transform + aux plane (+ prior network)
 static int cvae_chunk_front(bp_net* net, const float* tiles, const bp_transform_params* tp, int flags, int c0,
                             int nb, bool need_prior, cudaStream_t s, float** prior_out) {
+  ActRef in, res;
   const size_t HW = (size_t)net->H * net->W;
   const int mb = net->max_batch;
   int rc = launch_prepare(tiles + (size_t)c0 * HW, net->in_cat, 3 * (long long)HW, 1, 2, net->params + c0,
@@ -371,8 +455,10 @@ static int cvae_chunk_front(bp_net* net, const float* tiles, const bp_transform_
   if (rc != BP_OK) return rc;
   if (need_prior) {
     PostOp none;
-    rc = run_stack(net, ST_PRIOR, net->in_cat + HW, 3 * (long long)HW, nullptr, 0, none, nb, s, prior_out);
+    in.ptr = net->in_cat + HW; in.bs = 3 * (long long)HW;
+    rc = run_stack(net, ST_PRIOR, in, nullptr, 0, none, nb, s, &res);
     if (rc != BP_OK) return rc;
+    *prior_out = static_cast<float*>(const_cast<void*>(res.ptr));
   }
   return BP_OK;
 }
@@ -383,18 +469,19 @@ static int cvae_chunk_back(bp_net* net, const float* latent, const bp_transform_
   const size_t HW = (size_t)net->H * net->W;
   const size_t lhw = (size_t)net->lh * net->lw;
   PostOp none;
-  int rc = run_stack(net, ST_PZ, latent, (long long)lhw, net->in_cat, 3 * (long long)HW, none, nb, s, nullptr);
+  ActRef in, h;
+  in.ptr = latent; in.bs = (long long)lhw;
+  int rc = run_stack(net, ST_PZ, in, net->in_cat, 3 * (long long)HW, none, nb, s, nullptr);
   if (rc != BP_OK) return rc;
-  float* h = nullptr;
-  rc = run_stack(net, ST_PYZ, net->in_cat, 3 * (long long)HW, nullptr, 0, none, nb, s, &h);
+  in.ptr = net->in_cat; in.bs = 3 * (long long)HW;
+  rc = run_stack(net, ST_PYZ, in, nullptr, 0, none, nb, s, &h, net->st[ST_MU].layers[0].tc != nullptr);
   if (rc != BP_OK) return rc;
   PostOp post;
   if (flags & BP_FLAG_INVERSE) {
     post.post = POST_INV_SHIFT_LOG; post.sigma = net->params + net->max_batch + c0;
     post.k = tp->k_out; post.shift = tp->shift_out;
   }
-  const Stack& py = net->st[ST_PYZ];
-  return run_stack(net, ST_MU, h, (long long)py.out_c * py.OH * py.OW, out, (long long)HW, post, nb, s, nullptr);
+  return run_stack(net, ST_MU, h, out, (long long)HW, post, nb, s, nullptr);
 }
 
 static int cvae_paint_device(bp_net* net, const float* tiles, const float* latent, int mode, uint64_t seed,
@@ -459,8 +546,9 @@ static int cgan_paint_device(bp_net* net, const float* tiles, const bp_transform
       post.post = POST_INV_SHIFT_LOG; post.sigma = net->params + mb + c0;
       post.k = tp->k_out; post.shift = tp->shift_out;
     }
-    rc = run_stack(net, ST_GEN, net->in_cat, 2 * (long long)HW, out + (size_t)c0 * HW, (long long)HW, post, nb, s,
-                   nullptr);
+    ActRef in;
+    in.ptr = net->in_cat; in.bs = 2 * (long long)HW;
+    rc = run_stack(net, ST_GEN, in, out + (size_t)c0 * HW, (long long)HW, post, nb, s, nullptr);
     if (rc != BP_OK) return rc;
     if (net->debug) break;
   }
@@ -488,7 +576,8 @@ int bp_device_count(void) {
 int bp_cvae_create(const bp_cvae_desc* d, int precision, int max_batch, int device, bp_net** out) {
   BP_REQUIRE(d && out, BP_E_INVALID, "null argument");
   *out = nullptr;
-  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16, BP_E_INVALID, "bad precision %d", precision);
+  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16 || precision == BP_PREC_F16, BP_E_INVALID,
+             "bad precision %d", precision);
   BP_REQUIRE(max_batch > 0, BP_E_INVALID, "max_batch must be positive");
   BP_REQUIRE(d->tile_h > 0 && d->tile_w > 0 && d->latent_h > 0 && d->latent_w > 0, BP_E_INVALID, "bad tile shape");
   BP_REQUIRE((d->tile_h * d->tile_w) % 4 == 0, BP_E_INVALID, "tile area must be a multiple of 4");
@@ -541,7 +630,8 @@ int bp_cgan_create(const bp_layer_desc* layers, int n_layers, int tile_h, int ti
                    int device, bp_net** out) {
   BP_REQUIRE(layers && out && n_layers > 0, BP_E_INVALID, "null argument");
   *out = nullptr;
-  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16, BP_E_INVALID, "bad precision %d", precision);
+  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16 || precision == BP_PREC_F16, BP_E_INVALID,
+             "bad precision %d", precision);
   BP_REQUIRE(max_batch > 0 && tile_h > 0 && tile_w > 0 && (tile_h * tile_w) % 4 == 0, BP_E_INVALID, "bad shape");
   int rc = check_device(device);
   if (rc != BP_OK) return rc;
@@ -705,5 +795,42 @@ int bp_net_read_activation(bp_net* net, int stack, int layer, float* out, size_t
 }
 
 double bp_net_flops_per_tile(const bp_net* net) { return net ? net->flops_per_tile : 0.0; }
+
+int bp_net_set_profile(bp_net* net, int on) {
+  BP_REQUIRE(net, BP_E_INVALID, "null net");
+  for (auto& p : net->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  net->prof_events.clear();
+  net->prof_ids.clear();
+  net->profile = on != 0;
+  return BP_OK;
+}
+
+int bp_net_layer_info(const bp_net* net, int stack, int layer, double* flops, int* geom) {
+  BP_REQUIRE(net && stack >= 0 && stack < net->nstacks, BP_E_INVALID, "bad stack index");
+  BP_REQUIRE(layer >= 0 && (size_t)layer < net->st[stack].layers.size(), BP_E_INVALID, "bad layer index");
+  const Layer& l = net->st[stack].layers[layer];
+  if (flops) *flops = l.flops;
+  if (geom) {
+    geom[0] = l.d.kind; geom[1] = l.d.cin; geom[2] = l.d.cout; geom[3] = l.d.kernel; geom[4] = l.d.stride;
+    geom[5] = l.H; geom[6] = l.W; geom[7] = l.OHF; geom[8] = l.OWF; geom[9] = l.tc ? 1 : 0;
+  }
+  return BP_OK;
+}
+
+int bp_net_read_profile(bp_net* net, int stack, int layer, double* total_ms, int* launches) {
+  BP_REQUIRE(net && total_ms && launches, BP_E_INVALID, "null argument");
+  BP_CUDA_TRY(cudaSetDevice(net->device));
+  BP_CUDA_TRY(cudaDeviceSynchronize());
+  double ms = 0;
+  int cnt = 0;
+  for (size_t i = 0; i < net->prof_ids.size(); ++i) {
+    if (net->prof_ids[i] != stack * 1000 + layer) continue;
+    float t = 0.f;
+    BP_CUDA_TRY(cudaEventElapsedTime(&t, net->prof_events[i].first, net->prof_events[i].second));
+    ms += t; ++cnt;
+  }
+  *total_ms = ms; *launches = cnt;
+  return BP_OK;
+}
 
 }  // extern "C"

@@ -110,6 +110,11 @@ class _MetaUnpickler(pickle.Unpickler):
         if module in ("numpy", "numpy.core.multiarray", "numpy._core.multiarray") and name in (
                 "dtype", "scalar", "ndarray", "_reconstruct"):
             return getattr(_import_module(module), name)
+        if (module, name) == ("_codecs", "encode"):        # protocol-2 encoding of numpy scalar bytes
+            import codecs
+            return codecs.encode
+        if module.endswith(".__dict__") or name == "__dict__":
+            return {}
         if module == "builtins" and name in ("getattr", "tuple", "list", "dict", "set", "float", "int"):
             return getattr(importlib.import_module("builtins"), name)
         raise pickle.UnpicklingError("model_meta: refusing global %s.%s" % (module, name))

@@ -23,7 +23,9 @@ import numpy as np
 
 from . import _lib, arch as _arch, meta as _meta, transforms as _tf
 
-DEFAULT_PRECISION = os.environ.get("BARYON_PAINTER_PRECISION", "bf16")
+# "fp16": 16-bit operands on the tcgen05 tensor cores (default); "bf16": same kernels, bf16 operands;
+# "fp32": FFMA kernels.  See DESIGN.md "Precision" for why fp16 is the default 16-bit format.
+DEFAULT_PRECISION = os.environ.get("BARYON_PAINTER_PRECISION", "fp16")
 
 
 def _device_index(compute_device):
@@ -203,6 +205,9 @@ class CVAEPainter(Painter):
         Returns float32 (N,H,W) [(N,1,H,W) if ``inverse_transform=False``]."""
         tiles = np.asarray(tiles)
         n = tiles.shape[0]
+        if n == 0:
+            hw = tuple(self.model.dim_y[1:])
+            return np.empty((0, *hw) if inverse_transform else (0, 1, *hw), np.float32)
         zs = np.broadcast_to(np.asarray(z, np.float64).reshape(-1), (n,))
         use_t = bool(transform) and self.transform is not None
         use_i = bool(inverse_transform) and self.inverse_transform is not None

@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Headline benchmark: tiles/s painted by the fiducial CVAE (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--tiles 256]
+    python bench.py --impl reference ...      # the reference's CPU paint path on the host cores
+
+One step = one pass of the paint hot path over one batch of `--tiles` synthetic 512x512 DM tiles
+(seeded log-normal fields, fixed eps latents, z = 0) with seeded synthetic weights of the fiducial
+architecture (the trained blob is not in the reference checkout).  `value` times the device path
+with inputs resident in HBM (C ABI `bp_cvae_paint`, device pointers, CUDA events on the launching
+stream); `e2e` times the public `CVAEPainter.paint_batch` with host buffers, host<->device copies
+inside the timed region.  Under torchrun every rank paints its own `--tiles` tiles (weak scaling;
+the path has no collective), the time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_TILE = 20.254e9          # SURVEY.md section 8d / App. A (2*MACs of the 25 layers)
+TILE = 512
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops_sustained"], "bf16_tflops_burst": p["bf16_tflops"],
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json, sustained)"}
+    except Exception:
+        return {"bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+                "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0:
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(n_tiles, threads, warmup=1):
+    """The reference's CPU paint path (oracle port, bit-identical to the reference's torch modules)
+    as the reference would run a batch: a Python loop of batch-1 paint() calls."""
+    import torch
+    from oracle.cvae_oracle import CVAEOracle
+    from baryon_painter_b200 import arch, synthetic, transforms
+    torch.set_num_threads(threads)
+    A = arch.fiducial_cvae_architecture(TILE)
+    orc = CVAEOracle(A, synthetic.synthetic_cvae_state_dict(A, seed=0))
+    stats = transforms.fiducial_stats()
+    tiles = synthetic.synthetic_dm_tiles(n_tiles, TILE)
+    eps = synthetic.synthetic_latents(n_tiles)
+    for i in range(warmup):
+        orc.paint(tiles[0], 0.0, stats, eps=eps[0:1])
+    t0 = time.perf_counter()
+    for i in range(n_tiles):
+        orc.paint(tiles[i], 0.0, stats, eps=eps[i:i + 1])
+    dt = time.perf_counter() - t0
+    return n_tiles / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count()
+    sample = max(1, min(args.tiles, 8))
+    for _ in range(args.warmup):
+        cpu_baseline(1, threads, warmup=0)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        cpu_baseline(sample, threads, warmup=0)
+        n += sample
+    dt = time.perf_counter() - t0
+    v = n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "tiles/sec painted (fiducial CVAE)", "value": v, "unit": "tiles/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fiducial CVAE batched paint, %d synthetic 512x512 tiles, fixed latents, z=0"
+                               % args.tiles},
+        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
+                         "sample": "%d batch-1 paint() calls per step (oracle port of the reference torch-CPU "
+                                   "path, bit-identical to it in the build container)" % sample},
+        "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--tiles", type=int, default=256)
+    ap.add_argument("--precision", default=os.environ.get("BARYON_PAINTER_PRECISION", "fp16"))
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-tiles", type=int, default=6, help="tiles in the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-layers", action="store_true", help="print the per-layer timing table to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from baryon_painter_b200 import _lib, synthetic
+    from baryon_painter_b200.painter import CVAEPainter
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+    n = args.tiles
+    painter = CVAEPainter.synthetic(tile_size=TILE, seed=0, compute_device="cuda:%d" % local,
+                                    precision=args.precision, max_batch=n)
+    net = painter.model.net
+    tiles_h = synthetic.synthetic_dm_tiles(min(n, 16), TILE, seed0=1000 * rank)
+    tiles_h = np.concatenate([tiles_h] * ((n + len(tiles_h) - 1) // len(tiles_h)))[:n]
+    # distinct per-tile content without 256 RNG passes: scale the 16 base fields
+    tiles_h = np.ascontiguousarray(tiles_h * np.linspace(0.8, 1.25, n, dtype=np.float32)[:, None, None])
+    eps_h = synthetic.synthetic_latents(n, (TILE // 32, TILE // 32), seed=1 + rank)
+    zs = np.zeros(n)
+    s_in, s_out, tp = painter._sigmas(zs, True, True)
+    tparams = (s_in, s_out, zs.astype(np.float32), *tp)
+    flags = _lib.BP_FLAG_TRANSFORM | _lib.BP_FLAG_INVERSE
+    d_tiles = torch.from_numpy(tiles_h).cuda()
+    d_eps = torch.from_numpy(eps_h).cuda()
+    d_out = torch.empty((n, TILE, TILE), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        net.cvae_paint_device(d_tiles.data_ptr(), d_eps.data_ptr(), _lib.BP_LATENT_EPS, 0, tparams, flags,
+                              d_out.data_ptr(), n, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count(reset=True)
+    clocks = sampler.stop()
+    if not np.all(np.isfinite(d_out[:2].cpu().numpy())):
+        raise RuntimeError("non-finite painted tiles")
+
+    # ---- end to end through the public API, host buffers in and out
+    for _ in range(2):
+        painter.paint_batch(tiles_h, z=0.0, eps=eps_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_h = painter.paint_batch(tiles_h, z=0.0, eps=eps_h)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    total_tiles = n * args.steps * world
+
+    # ---- per-layer attribution (separate pass; event pairs around every layer launch)
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        net.set_profile(True)
+        step()
+        torch.cuda.synchronize()
+        rows = []
+        for sidx, name in enumerate(("prior_network", "p_z_in", "p_y_z_in", "p_mu_out")):
+            for li in range(len(painter.model.stacks[name])):
+                info = net.layer_info(sidx, li)
+                t_ms, cnt = net.read_profile(sidx, li)
+                rows.append((name, li, info, t_ms, cnt))
+        net.set_profile(False)
+        tot = sum(r[3] for r in rows) or 1.0
+        dom = [r for r in rows if r[2]["kernel"] == 3 and r[2]["cin"] == 128 and r[2]["cout"] == 128]
+        dom_ms = sum(r[3] for r in dom)
+        dom_fl = sum(r[2]["flops"] for r in dom) * n
+        dom_launches = sum(r[4] for r in dom) or 1
+        ach = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
+        whole = total_tiles / world * FLOPS_PER_TILE / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "3x3 128->128 @64x64 residual-block convolution (8 layers)",
+                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                "traffic": None, "peak_source": pk["source"], "launch_ms": dom_ms / dom_launches,
+                "share_of_step": dom_ms / tot,
+                "whole_net": {"achieved": whole, "frac": whole / pk["bf16_tflops"],
+                              "flops_per_tile": FLOPS_PER_TILE}}
+        if args.profile_layers:
+            for name, li, info, t_ms, cnt in rows:
+                tf = info["flops"] * n / (t_ms * 1e-3) / 1e12 if t_ms else 0
+                print("%-14s %2d  k%d s%d %3d->%3d @%3dx%-3d tensor=%d  %8.3f ms  %5.1f%%  %7.1f TFLOP/s" % (
+                    name, li, info["kernel"], info["stride"], info["cin"], info["cout"], info["H"], info["W"],
+                    info["tensor"], t_ms, 100 * t_ms / tot, tf), file=sys.stderr)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_baseline(args.cpu_tiles, os.cpu_count())
+        cpu = {"value": v, "unit": "tiles/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d of the %d tiles, batch-1 paint() loop as the reference runs it (%.1f s); oracle port of "
+                         "the reference torch-CPU path" % (args.cpu_tiles, n, dt)}
+    if rank == 0:
+        line = {
+            "metric": "tiles/sec painted (fiducial CVAE)", "value": total_tiles / (ms * 1e-3), "unit": "tiles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}.get(args.precision, args.precision), "data": "synthetic",
+            "config": {"workload": "fiducial CVAE batched paint, %d synthetic 512x512 tiles per GPU, fixed eps "
+                                   "latents, z=0 (BASELINE.json configs[1])" % n,
+                       "weights": "seeded synthetic state_dict, fiducial architecture (trained blob absent)",
+                       "l2": "inputs+outputs per step %.0f MB > 126 MB L2" % (2 * n * TILE * TILE * 4 / 1e6),
+                       "parallelism": "tiles sharded over %d GPU(s), no collective" % world},
+            "e2e": {"value": total_tiles / (e2e_ms * 1e-3), "unit": "tiles/s",
+                    "h2d_bytes_per_step": int(tiles_h.nbytes + eps_h.nbytes), "d2h_bytes_per_step": int(out_h.nbytes)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -58,8 +58,10 @@ enum { BP_RES_NONE = 0, BP_RES_OPEN = 1, BP_RES_CLOSE = 2 };
 
 /* arithmetic of the convolution stacks */
 enum {
-  BP_PREC_F32 = 0,   /* fp32 FFMA kernels; <= 1e-4 rel-L2 per tile vs the reference          */
-  BP_PREC_BF16 = 1   /* bf16 operands, fp32 accumulation on tcgen05; <= 1e-2 rel-L2 per tile */
+  BP_PREC_F32 = 0,   /* fp32 FFMA kernels; <= 1e-4 rel-L2 per tile vs the reference                  */
+  BP_PREC_BF16 = 1,  /* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma .kind::f16)            */
+  BP_PREC_F16 = 2    /* fp16 operands, same kernel and rate; 8x finer rounding than bf16 -- the
+                        16-bit path that holds <= 1e-2 rel-L2 through the exp(4x) inverse transform */
 };
 
 /* how the CVAE latent is obtained (reference cvae.py:63-66, 97-100, 149-155) */
@@ -159,6 +161,12 @@ int bp_stitch_finalize(const double* plane_num, const double* plane_den, double*
  * bp_net_set_debug(net, 1) before the paint call.  Used by the layer-boundary parity tests. */
 int bp_net_set_debug(bp_net* net, int keep_activations);
 int bp_net_read_activation(bp_net* net, int stack, int layer, float* out, size_t out_floats);
+/* per-layer timing: while on, every layer launch is bracketed by CUDA events on the launching
+ * stream (adds launch gaps -- use for attribution, never for throughput numbers) */
+int bp_net_set_profile(bp_net* net, int on);
+int bp_net_read_profile(bp_net* net, int stack, int layer, double* total_ms, int* launches);
+/* flops = 2*MACs per tile; geom[10] = {kind, cin, cout, kernel, stride, H, W, OH, OW, on_tensor_cores} */
+int bp_net_layer_info(const bp_net* net, int stack, int layer, double* flops, int* geom);
 /* kernels launched by this library on this thread since the last reset */
 int64_t bp_launch_count(int reset);
 /* algorithmic FLOPs (2*MACs) per tile of the network's convolutions */
