@@ -93,6 +93,7 @@ struct Layer {
   float* shift = nullptr;
   // 16-bit tensor-core path (filled by bp_tc.cu when the layer qualifies)
   void* tc = nullptr;
+  void* win = nullptr;           // windowed (gather-free) tensor-core kernel, bp_win.cu
   std::vector<float> host_weight;  // PyTorch-layout copy kept for the tensor-core packing
   double flops = 0;             // 2*MACs per sample (SURVEY App. A counting)
 };

@@ -123,6 +123,7 @@ int pack_layer(const bp_layer_desc& d, int H, int W, Layer* out) {
 void free_layer(Layer* l) {
   cudaFree(l->ktab); cudaFree(l->wmat); cudaFree(l->scale); cudaFree(l->shift);
   tc_free_layer(l);
+  win_free_layer(l);
   l->ktab = nullptr; l->wmat = nullptr; l->scale = nullptr; l->shift = nullptr;
 }
 
@@ -286,9 +287,11 @@ static int finish_create(bp_net* net) {
         if (!first) {
           // the producer of this layer's input must be a tensor-core layer too, unless we repack
           const Layer* prev = i > 0 ? &L[i - 1] : &net->st[ST_PYZ].layers.back();
-          if (!prev->tc && (L[i].d.cin % 8) != 0) continue;
+          if (!prev->tc && !prev->win && (L[i].d.cin % 8) != 0) continue;
         }
-        int rc = tc_pack_layer(&L[i], fmt);
+        int rc = BP_E_UNSUPPORTED;
+        if (win_layer_eligible(L[i].d, first)) rc = win_pack_layer(&L[i], fmt);
+        if (rc == BP_E_UNSUPPORTED) rc = tc_pack_layer(&L[i], fmt);
         if (rc != BP_OK) return rc;
       }
       // a residual block runs on one path only
@@ -297,8 +300,8 @@ static int finish_create(bp_net* net) {
           size_t j = i;
           while (L[j].d.res != BP_RES_CLOSE) ++j;
           bool all = true;
-          for (size_t q = i; q <= j; ++q) all = all && L[q].tc;
-          if (!all) for (size_t q = i; q <= j; ++q) tc_free_layer(&L[q]);
+          for (size_t q = i; q <= j; ++q) all = all && (L[q].tc || L[q].win);
+          if (!all) for (size_t q = i; q <= j; ++q) { tc_free_layer(&L[q]); win_free_layer(&L[q]); }
         }
     }
   }
@@ -354,7 +357,7 @@ static int run_stack(bp_net* net, int sidx, ActRef in, float* final_out, long lo
   for (int i = 0; i < nl; ++i) {
     Layer& l = st.layers[i];
     const bool last = (i == nl - 1);
-    const bool use_tc = l.tc != nullptr;
+    const bool use_tc = l.tc != nullptr || l.win != nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (net->profile) {
       BP_CUDA_TRY(cudaEventCreate(&e0)); BP_CUDA_TRY(cudaEventCreate(&e1));
@@ -382,7 +385,7 @@ static int run_stack(bp_net* net, int sidx, ActRef in, float* final_out, long lo
     if (last && final_out) {
       out.ptr = final_out; out.bs = final_bs; out.c8 = false;
     } else {
-      const bool next_tc = last ? c8_result_ok : (st.layers[i + 1].tc != nullptr);
+      const bool next_tc = last ? c8_result_ok : (st.layers[i + 1].tc != nullptr || st.layers[i + 1].win != nullptr);
       out.ptr = pick_buffer(net, cur.ptr, skip.ptr, in.ptr);
       BP_REQUIRE(out.ptr, BP_E_INVALID, "internal: no free activation buffer");
       out.c8 = use_tc && next_tc;
@@ -397,8 +400,10 @@ static int run_stack(bp_net* net, int sidx, ActRef in, float* final_out, long lo
         BP_REQUIRE(skip.c8, BP_E_INVALID, "internal: residual skip is not in the c8 layout");
         sk = skip.ptr;
       }
-      rc = launch_conv_tc(l, cur.ptr, out.c8 ? const_cast<void*>(out.ptr) : nullptr,
-                          out.c8 ? nullptr : static_cast<float*>(const_cast<void*>(out.ptr)), out.bs, sk, nb, s);
+      void* o16 = out.c8 ? const_cast<void*>(out.ptr) : nullptr;
+      float* o32 = out.c8 ? nullptr : static_cast<float*>(const_cast<void*>(out.ptr));
+      rc = l.win ? launch_conv_win(l, cur.ptr, o16, o32, out.bs, sk, nb, s)
+                 : launch_conv_tc(l, cur.ptr, o16, o32, out.bs, sk, nb, s);
     } else {
       ConvArgs a;
       memset(&a, 0, sizeof(a));
@@ -474,7 +479,7 @@ static int cvae_chunk_back(bp_net* net, const float* latent, const bp_transform_
   int rc = run_stack(net, ST_PZ, in, net->in_cat, 3 * (long long)HW, none, nb, s, nullptr);
   if (rc != BP_OK) return rc;
   in.ptr = net->in_cat; in.bs = 3 * (long long)HW;
-  rc = run_stack(net, ST_PYZ, in, nullptr, 0, none, nb, s, &h, net->st[ST_MU].layers[0].tc != nullptr);
+  rc = run_stack(net, ST_PYZ, in, nullptr, 0, none, nb, s, &h, net->st[ST_MU].layers[0].tc != nullptr || net->st[ST_MU].layers[0].win != nullptr);
   if (rc != BP_OK) return rc;
   PostOp post;
   if (flags & BP_FLAG_INVERSE) {
@@ -812,7 +817,7 @@ int bp_net_layer_info(const bp_net* net, int stack, int layer, double* flops, in
   if (flops) *flops = l.flops;
   if (geom) {
     geom[0] = l.d.kind; geom[1] = l.d.cin; geom[2] = l.d.cout; geom[3] = l.d.kernel; geom[4] = l.d.stride;
-    geom[5] = l.H; geom[6] = l.W; geom[7] = l.OHF; geom[8] = l.OWF; geom[9] = l.tc ? 1 : 0;
+    geom[5] = l.H; geom[6] = l.W; geom[7] = l.OHF; geom[8] = l.OWF; geom[9] = l.win ? 2 : (l.tc ? 1 : 0);
   }
   return BP_OK;
 }

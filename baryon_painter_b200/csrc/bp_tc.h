@@ -18,6 +18,12 @@ void tc_free_layer(Layer* l);
 // (out32: fp32 NCHW with per-sample stride out32_bs).
 int launch_conv_tc(const Layer& l, const void* in, void* out16, float* out32, long long out32_bs, const void* skip,
                    int nb, cudaStream_t s);
+// windowed kernel (bp_win.cu): stride-1 convolutions and transposed-convolution phases without gathers
+bool win_layer_eligible(const bp_layer_desc& d, bool first_in_sequence);
+int win_pack_layer(Layer* l, int fmt);
+void win_free_layer(Layer* l);
+int launch_conv_win(const Layer& l, const void* in, void* out16, float* out32, long long out32_bs, const void* skip,
+                    int nb, cudaStream_t s);
 int launch_pack_c8(const float* in, long long in_bs, int C, int hw, void* out, int nb, int fmt, cudaStream_t s);
 int launch_unpack_c8(const void* in, int C, int hw, float* out, long long out_bs, int nb, int fmt, cudaStream_t s);
 
