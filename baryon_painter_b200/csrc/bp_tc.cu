@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_f16(a.fmt, N);
+    const uint64_t a_tmpl = make_smem_desc(0, a.lbo_a, a.sbo_a), b_tmpl = make_smem_desc(0, a.lbo_b, a.sbo_b);
+    const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
       const int pi = tile / a.tiles_per_phase;
@@ -210,13 +212,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         mbar_wait(&full[s], par);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t aaddr = smem_u32(sA + s * TC_STAGE_BYTES);
-          const uint32_t baddr = smem_u32(sB + s * TC_STAGE_BYTES);
+          // descriptor templates + stage base in 16-byte units: two adds per MMA on the issuing thread
+          uint64_t da = a_tmpl + (uint64_t)(sA16 + s * (TC_STAGE_BYTES >> 4));
+          uint64_t db = b_tmpl + (uint64_t)(sB16 + s * (TC_STAGE_BYTES >> 4));
+          const uint32_t acc0 = kb != 0 ? 1u : 0u;
+          umma_f16(d_tmem, da, db, idesc, acc0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t da = make_smem_desc(aaddr + (uint32_t)j * 2u * 2048u, a.lbo_a, a.sbo_a);
-            const uint64_t db = make_smem_desc(baddr + (uint32_t)j * 2u * (uint32_t)N * 16u, a.lbo_b, a.sbo_b);
-            umma_f16(d_tmem, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+          for (int j = 1; j < 4; ++j) {
+            da += 256u;                       // 2 chunks x 128 rows x 16 B
+            db += 2u * (uint32_t)N;           // 2 chunks x N rows x 16 B
+            umma_f16(d_tmem, da, db, idesc, 1u);
           }
           umma_commit(&empty[s]);
           if (kb == nkb - 1) umma_commit(&tfull[as]);

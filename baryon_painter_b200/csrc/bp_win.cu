@@ -61,7 +61,7 @@ struct WinArgs {
   long long out32_bs;
   const uint4* skip;
   const uint4* wpack;
-  const int2* kstab;  // {A offset in 16 B units relative to the tile start inside a patch stage, LBO bytes}
+  const uint64_t* kstab;  // per k-step: A descriptor template (start field = offset of the tap/group in 16 B units)
   const float* scale;
   const float* shift;
   int H, W, cg_in;
@@ -77,6 +77,7 @@ struct WinArgs {
   float act_param;
   int fmt;
   uint32_t tmem_cols, patch_stage_bytes;
+  long long* timing;  // optional [grid][10] cycle counters (BP_WIN_TIMING=1), else null
 };
 
 __device__ __forceinline__ float win_act(float v, int act, float p) {
@@ -104,6 +105,17 @@ __device__ __forceinline__ float2 win_unpack16(uint32_t u, int fmt) {
   if (fmt == 0) return __half22float2(*reinterpret_cast<__half2*>(&u));
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
+
+#define TWAIT(slot, stmt)                                    \
+  do {                                                       \
+    if (a.timing) {                                          \
+      const long long _t0 = clock64();                       \
+      stmt;                                                  \
+      tacc[slot] += clock64() - _t0;                         \
+    } else {                                                 \
+      stmt;                                                  \
+    }                                                        \
+  } while (0)
 
 // region id -> coordinates (identical in every role)
 struct Region {
@@ -139,7 +151,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sP = smem;                                          // 2 patch stages
   uint8_t* sB = smem + 2 * a.patch_stage_bytes;                // WIN_BSTAGES weight stages
-  int2* s_ks = reinterpret_cast<int2*>(sB + WIN_BSTAGES * WIN_BSTAGE_BYTES);
+  uint64_t* s_ks = reinterpret_cast<uint64_t*>(sB + WIN_BSTAGES * WIN_BSTAGE_BYTES);
   float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_ks) + WIN_MAX_KS * 8);
   float* s_shift = s_scale + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 128);
@@ -153,6 +165,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N;
+  long long tacc[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
 
   for (int i = tid; i < a.total_ks; i += WIN_THREADS) s_ks[i] = a.kstab[i];
   for (int i = tid; i < 128; i += WIN_THREADS) {
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       const int nvalid = max(0, v_hi - v_lo);
       for (int blk = 0; blk < a.nblk; ++blk, ++pit) {
         const uint32_t st = pit & 1u, par = (pit >> 1) & 1u;
-        mbar_wait(&empty_p[st], par ^ 1u);
+        TWAIT(0, mbar_wait(&empty_p[st], par ^ 1u));
         uint4* stage = reinterpret_cast<uint4*>(sP + st * a.patch_stage_bytes);
         if (tid == 0) mbar_arrive_expect_tx(&full_p[st], (uint32_t)(a.gb * nvalid * ncopy) * 16u);
         const int items = a.gb * R.rows;
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
         const int nst = P.nks / 4;
         for (int sg = 0; sg < nst; ++sg, ++bit) {
           const uint32_t st = bit % WIN_BSTAGES, par = (bit / WIN_BSTAGES) & 1u;
-          mbar_wait(&empty_b[st], par ^ 1u);
+          TWAIT(0, mbar_wait(&empty_b[st], par ^ 1u));
           mbar_arrive_expect_tx(&full_b[st], b_bytes);
           bulk_g2s(sB + st * WIN_BSTAGE_BYTES, a.wpack + (size_t)(P.stage_begin + sg) * 8 * N, b_bytes, &full_b[st]);
         }
@@ -237,43 +251,67 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
+    // One lane issues every tcgen05.mma of the CTA, so the per-MMA instruction count of this loop is
+    // the kernel's critical path (a single thread retires a dependent instruction every ~4-6 cycles;
+    // the tensor pipe needs a new M=128 x N=128 MMA every 64).  Descriptors are therefore not built
+    // per MMA: the k-step table holds finished A-descriptor templates (LBO/SBO/version bits and the
+    // tap offset in the start-address field) and the loop only adds the patch/tile base (in 16-byte
+    // units; start-address fields never carry out of their 14 bits for addresses < 256 KB).
     const uint32_t idesc = make_idesc_f16(a.fmt, N);
+    const uint64_t* s_tmpl = reinterpret_cast<const uint64_t*>(s_ks);
+    const uint64_t db_tmpl = make_smem_desc(0, (uint32_t)N * 16u, 128u);
+    const uint32_t sB16 = smem_u32(sB) >> 4, sP16 = smem_u32(sP) >> 4;
+    const uint32_t pstage16 = a.patch_stage_bytes >> 4, bstage16 = WIN_BSTAGE_BYTES >> 4;
+    const uint32_t bstep16 = 2u * (uint32_t)N;           // one k-step of weights = 2 chunks x N rows x 16 B
+    const uint32_t tile_step = a.packed ? (uint32_t)(a.J * a.PW) : 128u;
+    const int T_r = a.T_r;
     uint32_t pit = 0, bit = 0, rcount = 0;
     for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x, ++rcount) {
       const Region R = decode_region(a, reg);
       const WinPhase P = a.phase[R.pi];
       const uint32_t as = rcount & 1u, apar = (rcount >> 1) & 1u;
-      mbar_wait(&tempty[as], apar ^ 1u);
+      TWAIT(0, mbar_wait(&tempty[as], apar ^ 1u));
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * (uint32_t)(a.T_r * N);
-      const int tile0 = a.packed ? 0 : (R.f0 - R.r_first * a.PW);   // patch-local flat offset of tile 0
-      const int tile_step = a.packed ? a.J * a.PW : 128;
+      const uint32_t d_tmem = tmem_base + as * (uint32_t)(T_r * N);
+      const uint32_t tile0 = a.packed ? 0u : (uint32_t)(R.f0 - R.r_first * a.PW);
+      const uint64_t* tmpl = s_tmpl + P.ks_begin;
       int ks = 0;
       for (int blk = 0; blk < a.nblk; ++blk, ++pit) {
         const uint32_t pst = pit & 1u, ppar = (pit >> 1) & 1u;
-        mbar_wait(&full_p[pst], ppar);
+        TWAIT(1, mbar_wait(&full_p[pst], ppar));
         tc_fence_after();
-        const uint32_t pbase = smem_u32(sP + pst * a.patch_stage_bytes);
+        const uint32_t a_add = sP16 + pst * pstage16 + tile0;
         const int ks_end = (blk == a.nblk - 1) ? P.nks : (blk + 1) * a.ks_per_blk;
-        for (; ks < ks_end; ++ks) {
+        while (ks < ks_end) {
+          // one weight stage = 4 k-steps (block boundaries are multiples of 4 except at the padded tail)
           const uint32_t bst = bit % WIN_BSTAGES, bpar = (bit / WIN_BSTAGES) & 1u;
-          if ((ks & 3) == 0) {
-            mbar_wait(&full_b[bst], bpar);
+          const int sub0 = ks & 3;
+          if (sub0 == 0) {
+            TWAIT(2, mbar_wait(&full_b[bst], bpar));
             tc_fence_after();
           }
+          const int nsub = min(4 - sub0, ks_end - ks);
           if (lane == 0) {
-            const int2 e = s_ks[P.ks_begin + ks];
-            const uint32_t baddr = smem_u32(sB + bst * WIN_BSTAGE_BYTES) + (uint32_t)(ks & 3) * 2u * (uint32_t)N * 16u;
-            const uint64_t db = make_smem_desc(baddr, (uint32_t)N * 16u, 128u);
-            for (int mt = 0; mt < a.T_r; ++mt) {
-              const uint32_t aaddr = pbase + (uint32_t)(tile0 + mt * tile_step + e.x) * 16u;
-              const uint64_t da = make_smem_desc(aaddr, (uint32_t)e.y, 128u);
-              umma_f16(d_tmem + (uint32_t)(mt * N), da, db, idesc, ks != 0 ? 1u : 0u);
+            const uint64_t db0 = db_tmpl + (uint64_t)(sB16 + bst * bstage16);
+            uint64_t t_next = tmpl[ks];
+            for (int q = 0; q < nsub; ++q) {
+              const uint64_t da0 = t_next + a_add;
+              if (q + 1 < nsub) t_next = tmpl[ks + q + 1];
+              const uint64_t db = db0 + (uint64_t)((uint32_t)(sub0 + q) * bstep16);
+              const uint32_t acc = (ks + q) != 0 ? 1u : 0u;
+              uint64_t da = da0;
+              uint32_t dt = d_tmem;
+              for (int mt = 0; mt < T_r; ++mt) {
+                umma_f16(dt, da, db, idesc, acc);
+                da += tile_step;
+                dt += (uint32_t)N;
+              }
             }
-            if ((ks & 3) == 3) umma_commit(&empty_b[bst]);
+            if (sub0 + nsub == 4) umma_commit(&empty_b[bst]);
           }
           __syncwarp();
-          if ((ks & 3) == 3) ++bit;
+          ks += nsub;
+          if (sub0 + nsub == 4) ++bit;
         }
         if (lane == 0) umma_commit(&empty_p[pst]);
         __syncwarp();
@@ -290,7 +328,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       const Region R = decode_region(a, reg);
       const WinPhase P = a.phase[R.pi];
       const uint32_t as = rcount & 1u, apar = (rcount >> 1) & 1u;
-      mbar_wait(&tfull[as], apar);
+      TWAIT(0, mbar_wait(&tfull[as], apar));
       tc_fence_after();
       const int m = ew * 32 + lane;
       for (int mt = 0; mt < a.T_r; ++mt) {
@@ -347,6 +385,15 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       mbar_arrive(&tempty[as]);
     }
   }
+  if (a.timing && lane == 0) {
+    // per CTA: [0] total, [1] patch producers wait empty_p, [2] weight producer wait empty_b,
+    // [3] mma wait tempty, [4] mma wait full_p, [5] mma wait full_b, [6] epilogue wait tfull
+    long long* t = a.timing + (size_t)blockIdx.x * 10;
+    if (warp == 0) { t[0] = clock64() - t_start; t[1] = tacc[0]; }
+    if (warp == 3) t[2] = tacc[0];
+    if (warp == 8) { t[3] = tacc[0]; t[4] = tacc[1]; t[5] = tacc[2]; }
+    if (warp == 4) t[6] = tacc[0];
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
@@ -360,7 +407,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
 // ------------------------------------------------------------------------------------------
 struct WinLayer {
   WinArgs proto;            // geometry / tables filled at pack time; pointers and nb at launch
-  int2* kstab = nullptr;
+  uint64_t* kstab = nullptr;
   uint4* wpack = nullptr;
   size_t smem = 0;
 };
@@ -455,7 +502,7 @@ int win_pack_layer(Layer* l, int fmt) {
   a.tmem_cols = cols;
 
   // k-step tables and packed weights
-  std::vector<int2> kstab;
+  std::vector<uint64_t> kstab;
   std::vector<uint16_t> wp;
   int stage_total = 0;
   for (int pi = 0; pi < l->nphase; ++pi) {
@@ -506,7 +553,7 @@ int win_pack_layer(Layer* l, int fmt) {
     wp.resize((size_t)(stage_total + P.nks / 4) * 8 * a.N * 8, 0);
     for (int ks = 0; ks < P.nks; ++ks) {
       if (ks >= real) {
-        kstab.push_back(make_int2(0, 16));              // zero weights; any in-bounds A address
+        kstab.push_back(make_smem_desc(0, 16, 128));    // zero weights; any in-bounds A address
         continue;
       }
       const Chunk c0 = steps[ks].first, c1 = steps[ks].second;
@@ -521,7 +568,8 @@ int win_pack_layer(Layer* l, int fmt) {
         lbo = a.PP * 16;
         BP_REQUIRE(lbo < (1 << 18), BP_E_UNSUPPORTED, "window kernel: group stride out of range");
       }
-      kstab.push_back(make_int2(a_off, lbo));
+      BP_REQUIRE(a_off >= 0 && a_off < 8192, BP_E_UNSUPPORTED, "window kernel: patch offset out of range");
+      kstab.push_back(make_smem_desc(0, (uint32_t)lbo, 128) + (uint64_t)a_off);
       const int stage = stage_total + ks / 4, kin = ks % 4;
       for (int half = 0; half < 2; ++half) {
         const Chunk c = half ? c1 : c0;
@@ -544,9 +592,9 @@ int win_pack_layer(Layer* l, int fmt) {
     return BP_E_UNSUPPORTED;
   }
   wl->smem = 2 * (size_t)a.patch_stage_bytes + WIN_FIXED_SMEM;
-  BP_CUDA_TRY(cudaMalloc(&wl->kstab, kstab.size() * sizeof(int2)));
+  BP_CUDA_TRY(cudaMalloc(&wl->kstab, kstab.size() * sizeof(uint64_t)));
   BP_CUDA_TRY(cudaMalloc(&wl->wpack, wp.size() * sizeof(uint16_t)));
-  BP_CUDA_TRY(cudaMemcpy(wl->kstab, kstab.data(), kstab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  BP_CUDA_TRY(cudaMemcpy(wl->kstab, kstab.data(), kstab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
   BP_CUDA_TRY(cudaMemcpy(wl->wpack, wp.data(), wp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   l->win = wl;
   return BP_OK;
@@ -588,9 +636,29 @@ int launch_conv_win(const Layer& l, const void* in, void* out16, float* out32, l
   a.nb = nb;
   a.total_regions = a.nphase * nb * a.nstrips * a.regs_per_strip;
   const int grid = std::min(a.total_regions, g_win_sms > 0 ? g_win_sms : 148);
+  static const bool timing = getenv("BP_WIN_TIMING") != nullptr;
+  static long long* d_timing = nullptr;
+  if (timing) {
+    if (!d_timing) BP_CUDA_TRY(cudaMalloc(&d_timing, sizeof(long long) * 10 * 256));
+    BP_CUDA_TRY(cudaMemsetAsync(d_timing, 0, sizeof(long long) * 10 * 256, s));
+    a.timing = d_timing;
+  }
   conv_win_kernel<<<grid, WIN_THREADS, wl->smem, s>>>(a);
   launch_counter()++;
   BP_CUDA_TRY(cudaGetLastError());
+  if (timing) {
+    BP_CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<long long> h(10 * 256);
+    BP_CUDA_TRY(cudaMemcpy(h.data(), d_timing, sizeof(long long) * 10 * 256, cudaMemcpyDeviceToHost));
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < grid; ++c)
+      for (int q = 0; q < 7; ++q) acc[q] += (double)h[c * 10 + q] / grid;
+    fprintf(stderr,
+            "[win] cin=%d cout=%d k=%d H=%d N=%d T_r=%d regions/cta=%.1f total=%.0f cyc | waits: patch-prod %.0f "
+            "w-prod %.0f mma:tempty %.0f mma:full_p %.0f mma:full_b %.0f epi:tfull %.0f\n",
+            l.d.cin, l.d.cout, l.d.kernel, l.H, a.N, a.T_r, (double)a.total_regions / grid, acc[0], acc[1], acc[2],
+            acc[3], acc[4], acc[5], acc[6]);
+  }
   return BP_OK;
 }
 
