@@ -94,7 +94,9 @@ struct Layer {
   // 16-bit tensor-core path (filled by bp_tc.cu when the layer qualifies)
   void* tc = nullptr;
   void* win = nullptr;           // windowed (gather-free) tensor-core kernel, bp_win.cu
+  bool v2 = false;               // runs on the window-GEMM engine (bp_wconv.cu)
   std::vector<float> host_weight;  // PyTorch-layout copy kept for the tensor-core packing
+  std::vector<float> host_scale, host_shift;
   double flops = 0;             // 2*MACs per sample (SURVEY App. A counting)
 };
 

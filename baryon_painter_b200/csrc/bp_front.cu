@@ -1,0 +1,247 @@
+// Elementwise / stencil ends of the 16-bit paint path (HBM-bound passes, coalesced and vectorised):
+//
+//   front_prior_kernel    raw DM tile -> forward transform y = ln(x/sigma + 1)/k - shift  -> [y, z] written in the
+//                         shifted space-to-depth NHWC layout prior_network.0 (k4 s2) reads
+//                         (reference data_transforms.py:66-76 + models/utils.py:159-182 merge_aux_label)
+//   front_latent_kernel   latent (h x w) -> p_z_in (three 1->1 transposed convolutions + BN + ReLU, fp32, whole
+//                         pyramid recomputed per CTA in shared memory) and, fused, the forward transform again:
+//                         writes the decoder input pixel [p_z_in(latent), y, z, 0] as one 8-byte NHWC store
+//                         (reference cvae.py:104-109: merge_aux_label + p_z_in + torch.cat)
+//   tail_stencil_kernel   last 1->1 convolution + activation (Softplus) + inverse transform
+//                         (exp((x + shift)*k) - 1)*sigma  -> fp32 tile  (reference data_transforms.py:88-98)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "bp_front.h"
+
+namespace bp {
+
+__device__ __forceinline__ uint16_t f_to16(float v, int fmt) {
+  if (fmt == 0) {
+    __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__device__ __forceinline__ float f_transform(float x, float sigma, float k, float shift, int on) {
+  return on ? logf(x / sigma + 1.f) / k - shift : x;
+}
+
+// ---- prior input: [y, z, 0, 0] per pixel, space-to-depth block 2 (pixel (y,x) -> block ((y+1)/2, (x+1)/2)) ----
+__global__ void front_prior_kernel(const float* __restrict__ tiles, uint2* __restrict__ out, const float* __restrict__ sigma,
+                                   const float* __restrict__ aux, float k_in, float shift_in, int do_t, int H, int W, int b,
+                                   int fmt) {
+  const int n = blockIdx.z;
+  const float sg = do_t ? sigma[n] : 1.f;
+  const uint16_t z16 = f_to16(aux[n], fmt);
+  const int hw = H * W;
+  const int Hs = b > 1 ? H / b + 1 : H, Ws = b > 1 ? W / b + 1 : W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    const int y = p / W, x = p - y * W;
+    const float v = f_transform(tiles[(size_t)n * hw + p], sg, k_in, shift_in, do_t);
+    size_t o;
+    if (b == 1) {
+      o = (size_t)n * hw + p;
+    } else {
+      const int yy = y + (b >> 1), xx = x + (b >> 1);
+      const int by = yy / b, sy = yy - by * b, bx = xx / b, sx = xx - bx * b;
+      o = ((((size_t)n * Hs + by) * Ws + bx) * b + sy) * b + sx;
+    }
+    out[o] = make_uint2((uint32_t)f_to16(v, fmt) | ((uint32_t)z16 << 16), 0u);
+  }
+}
+
+int launch_front_prior(const float* tiles, const ActDesc& out, const float* sigma, const float* aux, float k_in,
+                       float shift_in, int do_transform, int nb, int fmt, cudaStream_t s) {
+  BP_REQUIRE(out.Cp == 4 && !out.f32, BP_E_INVALID, "front_prior: output must be a 4-channel NHWC tensor");
+  const int hw = out.H * out.W;
+  const int bx = std::min(256, (hw + 255) / 256);
+  front_prior_kernel<<<dim3(bx, 1, nb), 256, 0, s>>>(tiles, static_cast<uint2*>(out.ptr), sigma, aux, k_in, shift_in,
+                                                     do_transform, out.H, out.W, out.b, fmt);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+// ---- decoder input ---------------------------------------------------------------------------------
+// 1 -> 1 channel transposed convolution with k = 2s, p = s/2: two taps per dimension
+__device__ __forceinline__ float up_at(const float* in, int ih, int iw, const float* w, int k, int s, int p, int oy, int ox) {
+  const int r0 = (oy + p) % s, qh = (oy + p) / s, c0 = (ox + p) % s, qw = (ox + p) / s;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int iy = qh - a;
+    if (iy < 0 || iy >= ih) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ix = qw - b;
+      if (ix < 0 || ix >= iw) continue;
+      acc = fmaf(in[iy * iw + ix], w[(r0 + s * a) * k + (c0 + s * b)], acc);
+    }
+  }
+  return acc;
+}
+__device__ __forceinline__ float f_act(float v, int act, float p) {
+  switch (act) {
+    case BP_ACT_RELU: return fmaxf(v, 0.f);
+    case BP_ACT_LEAKY:
+    case BP_ACT_PRELU: return v >= 0.f ? v : v * p;
+    case BP_ACT_SOFTPLUS: return v > 20.f ? v : log1pf(expf(v));
+    case BP_ACT_TANH: return tanhf(v);
+    case BP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// one CTA = one band of `rows` output rows of one tile.  Levels 0 .. nl-2 of the pyramid are recomputed per CTA
+// for the rows the band needs (the whole pyramid of a tile is 2 MFLOP); the last level is fused with the store.
+__global__ void __launch_bounds__(256) front_latent_kernel(const float* __restrict__ tiles, const float* __restrict__ latent,
+                                                           uint2* __restrict__ out, const float* __restrict__ sigma,
+                                                           const float* __restrict__ aux, const PzParams pz, float k_in,
+                                                           float shift_in, int do_t, int H, int W, int lh, int lw, int rows,
+                                                           int fmt) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y;
+  const int y0 = blockIdx.x * rows;
+  // level geometry
+  int lvh[5], lvw[5];
+  lvh[0] = lh; lvw[0] = lw;
+  for (int i = 0; i < pz.nl; ++i) { lvh[i + 1] = lvh[i] * pz.s[i]; lvw[i + 1] = lvw[i] * pz.s[i]; }
+  // row ranges needed at every level (inclusive), from the band downwards
+  int lo[5], hi[5];
+  lo[pz.nl] = y0; hi[pz.nl] = min(H, y0 + rows) - 1;
+  for (int i = pz.nl - 1; i >= 0; --i) {
+    lo[i] = max(0, (lo[i + 1] + pz.p[i]) / pz.s[i] - 1);
+    hi[i] = min(lvh[i] - 1, (hi[i + 1] + pz.p[i]) / pz.s[i]);
+  }
+  // shared buffers: level i rows [lo[i], hi[i]] x lvw[i]
+  float* buf[5];
+  {
+    float* q = sm;
+    for (int i = 0; i < pz.nl; ++i) { buf[i] = q; q += (hi[i] - lo[i] + 1) * lvw[i]; }
+  }
+  for (int i = threadIdx.x; i < (hi[0] - lo[0] + 1) * lvw[0]; i += blockDim.x)
+    buf[0][i] = latent[(size_t)n * lh * lw + (size_t)lo[0] * lw + i];
+  __syncthreads();
+  for (int l = 0; l + 1 < pz.nl; ++l) {
+    const int nr = hi[l + 1] - lo[l + 1] + 1, w1 = lvw[l + 1];
+    for (int i = threadIdx.x; i < nr * w1; i += blockDim.x) {
+      const int oy = lo[l + 1] + i / w1, ox = i % w1;
+      // rows of the source buffer are offset by lo[l]
+      const float v = up_at(buf[l] - (size_t)lo[l] * lvw[l], hi[l] + 1, lvw[l], pz.w[l], pz.k[l], pz.s[l], pz.p[l], oy, ox);
+      buf[l + 1][i] = f_act(fmaf(v, pz.scale[l], pz.shift[l]), pz.act[l], pz.act_param[l]);
+    }
+    __syncthreads();
+  }
+  const int L = pz.nl - 1;
+  const float sg = do_t ? sigma[n] : 1.f;
+  const uint16_t z16 = f_to16(aux[n], fmt);
+  const int nr = hi[pz.nl] - lo[pz.nl] + 1;
+  for (int i = threadIdx.x; i < nr * W; i += blockDim.x) {
+    const int oy = y0 + i / W, ox = i % W;
+    float v = up_at(buf[L] - (size_t)lo[L] * lvw[L], hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], pz.p[L], oy, ox);
+    v = f_act(fmaf(v, pz.scale[L], pz.shift[L]), pz.act[L], pz.act_param[L]);
+    const size_t p = ((size_t)n * H + oy) * W + ox;
+    const float yv = f_transform(tiles[p], sg, k_in, shift_in, do_t);
+    out[p] = make_uint2((uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(yv, fmt) << 16), (uint32_t)z16);
+  }
+}
+
+int launch_front_latent(const float* tiles, const float* latent, const ActDesc& out, const float* sigma, const float* aux,
+                        const PzParams& pz, float k_in, float shift_in, int do_transform, int lh, int lw, int nb, int fmt,
+                        cudaStream_t s) {
+  BP_REQUIRE(out.Cp == 4 && out.b == 1 && !out.f32, BP_E_INVALID, "front_latent: output must be a plain 4-channel NHWC tensor");
+  const int rows = 16;
+  // shared memory: every level's needed rows (upper bound: rows/stride products + 2 per level)
+  size_t fl = 0;
+  {
+    int h = lh, w = lw, need = rows;
+    std::vector<int> hs{h}, ws{w};
+    for (int i = 0; i < pz.nl; ++i) { h *= pz.s[i]; w *= pz.s[i]; hs.push_back(h); ws.push_back(w); }
+    for (int i = pz.nl - 1; i >= 0; --i) {
+      need = std::min(hs[i], need / pz.s[i] + 3);
+      fl += (size_t)need * ws[i];
+    }
+  }
+  const size_t smem = fl * sizeof(float);
+  BP_REQUIRE(smem <= 96 * 1024, BP_E_UNSUPPORTED, "front_latent: pyramid band needs %zu bytes of shared memory", smem);
+  static bool attr = false;
+  if (!attr) {
+    BP_CUDA_TRY(cudaFuncSetAttribute(front_latent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  front_latent_kernel<<<dim3((out.H + rows - 1) / rows, nb), 256, smem, s>>>(
+      tiles, latent, static_cast<uint2*>(out.ptr), sigma, aux, pz, k_in, shift_in, do_transform, out.H, out.W, lh, lw, rows,
+      fmt);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+// ---- tail: 1 -> 1 channel k x k convolution (fp32) + activation + inverse transform ------------------
+template <int K>
+__global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           long long out_bs, const TailParams tp,
+                                                           const float* __restrict__ post_sigma, int H, int W) {
+  constexpr int R = K / 2;
+  constexpr int TX = 64, TY = 16;                 // tile of outputs per CTA; 4 outputs per thread along x
+  __shared__ float sh[TY + 2 * R][TX + 2 * R + 1];
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const float* src = in + (size_t)n * H * W;
+  for (int i = threadIdx.x; i < (TY + 2 * R) * (TX + 2 * R); i += blockDim.x) {
+    const int ly = i / (TX + 2 * R), lx = i - ly * (TX + 2 * R);
+    const int y = y0 + ly - R, x = x0 + lx - R;
+    sh[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (size_t)y * W + x) : 0.f;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / 16, tx = (threadIdx.x % 16) * 4;
+  const int y = y0 + ty;
+  if (y >= H) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < K; ++r)
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const float w = tp.w[r * K + q];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = fmaf(sh[ty + r][tx + e + q], w, acc[e]);
+    }
+  const float sg = tp.post ? post_sigma[n] : 1.f;
+  float o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v = f_act(fmaf(acc[e], tp.scale, tp.shift), tp.act, tp.act_param);
+    if (tp.post) v = (expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+    o[e] = v;
+  }
+  float* dst = out + (size_t)n * out_bs + (size_t)y * W + x0 + tx;
+  if (x0 + tx + 3 < W && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (x0 + tx + e < W) dst[e] = o[e];
+  }
+}
+
+int launch_tail_stencil(const float* in, float* out, long long out_bs, const TailParams& tp, const float* post_sigma, int H,
+                        int W, int nb, cudaStream_t s) {
+  const dim3 grid((W + 63) / 64, (H + 15) / 16, nb);
+  switch (tp.k) {
+    case 1: tail_stencil_kernel<1><<<grid, 256, 0, s>>>(in, out, out_bs, tp, post_sigma, H, W); break;
+    case 3: tail_stencil_kernel<3><<<grid, 256, 0, s>>>(in, out, out_bs, tp, post_sigma, H, W); break;
+    case 5: tail_stencil_kernel<5><<<grid, 256, 0, s>>>(in, out, out_bs, tp, post_sigma, H, W); break;
+    case 7: tail_stencil_kernel<7><<<grid, 256, 0, s>>>(in, out, out_bs, tp, post_sigma, H, W); break;
+    default:
+      set_error("tail stencil: kernel size %d", tp.k);
+      return BP_E_UNSUPPORTED;
+  }
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+}  // namespace bp

@@ -13,6 +13,8 @@
 
 #include "bp_common.h"
 #include "bp_tc.h"
+#include "bp_wconv.h"
+#include "bp_front.h"
 
 namespace bp {
 
@@ -109,6 +111,7 @@ int pack_layer(const bp_layer_desc& d, int H, int W, Layer* out) {
   std::vector<float> scale(d.cout, 1.f), shift(d.cout, 0.f);
   if (d.scale) memcpy(scale.data(), d.scale, sizeof(float) * d.cout);
   if (d.shift) memcpy(shift.data(), d.shift, sizeof(float) * d.cout);
+  l.host_scale = scale; l.host_shift = shift;
   BP_CUDA_TRY(cudaMalloc(&l.ktab, ktab.size() * sizeof(int4)));
   BP_CUDA_TRY(cudaMalloc(&l.wmat, wmat.size() * sizeof(float)));
   BP_CUDA_TRY(cudaMalloc(&l.scale, d.cout * sizeof(float)));
@@ -144,6 +147,29 @@ struct Stack {
 enum { NET_CVAE = 0, NET_CGAN = 1 };
 enum { ST_PRIOR = 0, ST_PZ = 1, ST_PYZ = 2, ST_MU = 3, ST_GEN = 0 };
 
+// ---- execution plan of the 16-bit window-GEMM engine (bp_wconv.cu) ------------------------------
+enum { V2_WCONV = 0, V2_F32CONV = 1, V2_TO_NHWC16 = 2, V2_TO_F32 = 3, V2_TAIL = 4 };
+struct V2Op {
+  int kind = V2_WCONV;
+  int stack = -1, index = -1;     // layer this op executes (-1: layout conversion)
+  Layer* l = nullptr;
+  WLayer* w = nullptr;
+  int in = -1, out = -1, skip = -1;
+  bool final = false;             // writes the caller's output buffer (with the fused inverse transform)
+};
+struct V2Plan {
+  bool built = false;
+  std::vector<ActDesc> acts;
+  std::vector<V2Op> ops;          // decoder: p_y_z_in + p_mu_out
+  std::vector<V2Op> prior_ops;    // prior_network (when it lowers to window GEMMs)
+  std::vector<void*> owned;
+  bool front_on = false;          // fused transform + p_z_in + NHWC pack feeds the decoder
+  bool prior_on = false;
+  int dec_in = -1, prior_in = -1, prior_out = -1;
+  PzParams pz;
+  TailParams tail;
+};
+
 struct bp_net {
   int device = 0, kind = NET_CVAE, prec = BP_PREC_F32, max_batch = 0, chunk = 0;
   int H = 0, W = 0, lh = 0, lw = 0, in_c = 0;
@@ -171,6 +197,7 @@ struct bp_net {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per recorded layer launch
   std::vector<int> prof_ids;                                     // stack*1000 + layer
   double flops_per_tile = 0;
+  V2Plan v2;
 };
 
 static int build_stack(const bp_layer_desc* descs, int n, int in_c, int H, int W, Stack* st, const char* name) {
@@ -208,6 +235,9 @@ static void destroy_net(bp_net* net) {
     for (auto& l : net->st[s].layers) free_layer(&l);
     for (float* p : net->dbg[s]) cudaFree(p);
   }
+  for (auto& op : net->v2.ops) wconv_free(op.w);
+  for (auto& op : net->v2.prior_ops) wconv_free(op.w);
+  for (void* p : net->v2.owned) cudaFree(p);
   cudaFree(net->in_cat);
   for (int i = 0; i < 4; ++i) cudaFree(net->pool[i]);
   cudaFree(net->latent); cudaFree(net->prior_all); cudaFree(net->prior_keep); cudaFree(net->params);
@@ -239,6 +269,8 @@ static int check_device(int device) {
   return BP_OK;
 }
 
+static int v2_build(bp_net* net);
+
 static int finish_create(bp_net* net) {
   const size_t HW = (size_t)net->H * net->W;
   size_t mx = 0;
@@ -249,7 +281,7 @@ static int finish_create(bp_net* net) {
   }
   // chunk: keep the three rotating activation buffers of one chunk around L2 size (126 MB) so that
   // a layer's output is still cache-resident when the next layer reads it
-  int chunk = net->prec == BP_PREC_F32 ? 4 : 8;
+  int chunk = net->prec == BP_PREC_F32 ? 4 : 64;
   if (const char* e = getenv("BP_CHUNK")) chunk = std::max(1, atoi(e));
   net->chunk = std::min(chunk, net->max_batch);
   net->pool_floats = mx * net->chunk;
@@ -304,7 +336,185 @@ static int finish_create(bp_net* net) {
           if (!all) for (size_t q = i; q <= j; ++q) { tc_free_layer(&L[q]); win_free_layer(&L[q]); }
         }
     }
+    if (net->kind == NET_CVAE && !getenv("BP_ENGINE_V1")) {
+      int rc = v2_build(net);
+      if (rc != BP_OK) return rc;
+    }
   }
+  return BP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// 16-bit engine, version 2: decoder (p_y_z_in + p_mu_out) as a chain of window GEMMs over NHWC
+// activations; every layer output has its own zero-initialised buffer (space-to-depth borders are
+// the zero padding of the consumer and are never written)
+// ------------------------------------------------------------------------------------------
+static int v2_new_act(bp_net* net, ActDesc d, int* idx) {
+  void* p = nullptr;
+  const size_t bytes = d.bytes_per_sample() * (size_t)net->chunk + 4096;   // slack: 16-byte vector tails
+  BP_CUDA_TRY(cudaMalloc(&p, bytes));
+  BP_CUDA_TRY(cudaMemset(p, 0, bytes));
+  d.ptr = p;
+  net->v2.owned.push_back(p);
+  net->v2.acts.push_back(d);
+  *idx = (int)net->v2.acts.size() - 1;
+  return BP_OK;
+}
+
+struct V2Ref { int stack, index; Layer* l; bool w; int need_b; };
+
+// lowers one layer sequence starting from act `cur`; the last layer of a `caller_out` sequence writes the
+// caller's fp32 tiles (tail stencil or fp32 kernel, inverse transform fused)
+static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vector<V2Op>& ops, bool caller_out,
+                        int* last_act) {
+  V2Plan& P = net->v2;
+  const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
+  if (caller_out) seq.back().w = false;
+  for (size_t i = 0; i < seq.size(); ++i)
+    if (seq[i].l->d.res == BP_RES_OPEN) {
+      size_t j = i;
+      while (seq[j].l->d.res != BP_RES_CLOSE) ++j;
+      bool all = true;
+      for (size_t q = i; q <= j; ++q) all = all && seq[q].w;
+      for (size_t q = i; q <= j; ++q) seq[q].w = all;
+    }
+  int skip = -1;
+  for (size_t i = 0; i < seq.size(); ++i) {
+    V2Ref& r = seq[i];
+    const bp_layer_desc& d = r.l->d;
+    const bool last = (i + 1 == seq.size());
+    V2Op op;
+    op.stack = r.stack; op.index = r.index; op.l = r.l;
+    if (r.w) {
+      const int Cp = v2_padc(d.cin);
+      if (P.acts[cur].f32) {
+        ActDesc a; a.C = d.cin; a.Cp = Cp; a.H = r.l->H; a.W = r.l->W; a.b = r.need_b;
+        V2Op cv; cv.kind = V2_TO_NHWC16; cv.in = cur;
+        int rc = v2_new_act(net, a, &cv.out);
+        if (rc != BP_OK) return rc;
+        ops.push_back(cv);
+        cur = cv.out;
+      }
+      BP_REQUIRE(P.acts[cur].b == r.need_b && P.acts[cur].Cp == Cp, BP_E_INVALID,
+                 "internal: layer %d.%d reads layout b=%d Cp=%d, producer wrote b=%d Cp=%d", r.stack, r.index,
+                 r.need_b, Cp, P.acts[cur].b, P.acts[cur].Cp);
+      if (d.res == BP_RES_OPEN) skip = cur;
+      ActDesc o; o.C = d.cout; o.H = r.l->OHF; o.W = r.l->OWF;
+      const bool next_w = !last && seq[i + 1].w;
+      if (d.cout == 1) { o.f32 = true; o.Cp = 1; }
+      else { o.Cp = v2_padc(d.cout); o.b = next_w ? seq[i + 1].need_b : 1; }
+      std::vector<WSpec> cands;
+      int rc = v2_candidates(*r.l, fmt, Cp, &cands);
+      if (rc != BP_OK) return rc;
+      rc = BP_E_UNSUPPORTED;
+      for (const WSpec& sp : cands) {
+        rc = wconv_build(sp, P.acts[cur], net->chunk, &op.w);
+        if (rc != BP_E_UNSUPPORTED) break;
+      }
+      if (rc != BP_OK) return rc;
+      op.kind = V2_WCONV; op.in = cur;
+      r.l->v2 = true;
+      if (d.res == BP_RES_CLOSE) { op.skip = skip; skip = -1; }
+      rc = v2_new_act(net, o, &op.out);
+      if (rc != BP_OK) return rc;
+      ops.push_back(op);
+      cur = op.out;
+    } else {
+      if (!P.acts[cur].f32) {
+        ActDesc a; a.C = d.cin; a.Cp = d.cin; a.H = r.l->H; a.W = r.l->W; a.f32 = true;
+        V2Op cv; cv.kind = V2_TO_F32; cv.in = cur;
+        int rc = v2_new_act(net, a, &cv.out);
+        if (rc != BP_OK) return rc;
+        ops.push_back(cv);
+        cur = cv.out;
+      }
+      if (d.res == BP_RES_OPEN) skip = cur;
+      op.kind = V2_F32CONV; op.in = cur; op.final = last && caller_out;
+      if (op.final && d.kind == BP_CONV && d.cin == 1 && d.cout == 1 && d.stride == 1 && d.kernel == 2 * d.pad + 1 &&
+          d.kernel <= 7 && d.res == BP_RES_NONE && !getenv("BP_V2_NOTAIL")) {
+        op.kind = V2_TAIL;
+        TailParams& t = P.tail;
+        memset(&t, 0, sizeof(t));
+        t.k = d.kernel;
+        for (int q = 0; q < d.kernel * d.kernel; ++q) t.w[q] = r.l->host_weight[q];
+        t.scale = r.l->host_scale[0]; t.shift = r.l->host_shift[0];
+        t.act = d.act; t.act_param = d.act_param;
+      }
+      if (d.res == BP_RES_CLOSE) { op.skip = skip; skip = -1; }
+      if (!op.final) {
+        ActDesc o; o.C = d.cout; o.Cp = d.cout; o.H = r.l->OHF; o.W = r.l->OWF; o.f32 = true;
+        int rc = v2_new_act(net, o, &op.out);
+        if (rc != BP_OK) return rc;
+        cur = op.out;
+      }
+      ops.push_back(op);
+    }
+  }
+  if (last_act) *last_act = cur;
+  return BP_OK;
+}
+
+static int v2_build(bp_net* net) {
+  V2Plan& P = net->v2;
+  // ---- decoder
+  std::vector<V2Ref> seq;
+  for (int sidx : {ST_PYZ, ST_MU})
+    for (size_t i = 0; i < net->st[sidx].layers.size(); ++i) {
+      V2Ref r{sidx, (int)i, &net->st[sidx].layers[i], false, 1};
+      r.w = v2_eligible(*r.l, &r.need_b);
+      seq.push_back(r);
+    }
+  // fused front: p_z_in is a pyramid of single-channel k = 2s transposed convolutions
+  const std::vector<Layer>& pzl = net->st[ST_PZ].layers;
+  bool front = seq[0].w && seq[0].need_b == 1 && net->in_c == 3 && pzl.size() <= 4 && !getenv("BP_V2_NOFRONT");
+  for (const Layer& l : pzl)
+    front = front && l.d.kind == BP_CONVT && l.d.cin == 1 && l.d.cout == 1 && l.d.kernel == 2 * l.d.stride &&
+            2 * l.d.pad == l.d.stride && l.d.kernel <= 8 && l.d.out_pad == 0 && l.d.res == BP_RES_NONE;
+  int start;
+  if (front) {
+    memset(&P.pz, 0, sizeof(P.pz));
+    P.pz.nl = (int)pzl.size();
+    for (int i = 0; i < P.pz.nl; ++i) {
+      const Layer& l = pzl[i];
+      P.pz.k[i] = l.d.kernel; P.pz.s[i] = l.d.stride; P.pz.p[i] = l.d.pad; P.pz.act[i] = l.d.act;
+      P.pz.act_param[i] = l.d.act_param; P.pz.scale[i] = l.host_scale[0]; P.pz.shift[i] = l.host_shift[0];
+      for (int q = 0; q < l.d.kernel * l.d.kernel; ++q) P.pz.w[i][q] = l.host_weight[q];
+    }
+    ActDesc a; a.C = 3; a.Cp = 4; a.H = net->H; a.W = net->W; a.b = 1;
+    int rc = v2_new_act(net, a, &start);
+    if (rc != BP_OK) return rc;
+    P.front_on = true;
+  } else {
+    // the assembled decoder input [latent plane, y, z plane], fp32 NCHW (written by prepare + p_z_in)
+    ActDesc in0;
+    in0.ptr = net->in_cat; in0.C = net->in_c; in0.Cp = net->in_c; in0.H = net->H; in0.W = net->W; in0.f32 = true;
+    P.acts.push_back(in0);
+    start = (int)P.acts.size() - 1;
+  }
+  P.dec_in = start;
+  int rc = v2_build_seq(net, seq, start, P.ops, true, nullptr);
+  if (rc != BP_OK) return rc;
+  // ---- prior network
+  std::vector<Layer>& prl = net->st[ST_PRIOR].layers;
+  if (!prl.empty() && !getenv("BP_V2_NOPRIOR")) {
+    std::vector<V2Ref> ps;
+    for (size_t i = 0; i < prl.size(); ++i) {
+      V2Ref r{ST_PRIOR, (int)i, &prl[i], false, 1};
+      r.w = v2_eligible(*r.l, &r.need_b);
+      ps.push_back(r);
+    }
+    if (ps[0].w && prl[0].d.cin == 2) {
+      ActDesc a; a.C = 2; a.Cp = 4; a.H = net->H; a.W = net->W; a.b = ps[0].need_b;
+      rc = v2_new_act(net, a, &P.prior_in);
+      if (rc != BP_OK) return rc;
+      rc = v2_build_seq(net, ps, P.prior_in, P.prior_ops, false, &P.prior_out);
+      if (rc != BP_OK) return rc;
+      BP_REQUIRE(P.acts[P.prior_out].f32, BP_E_INVALID, "internal: prior head is not fp32");
+      P.prior_on = true;
+    }
+  }
+  P.built = true;
   return BP_OK;
 }
 
@@ -435,6 +645,83 @@ static int run_stack(bp_net* net, int sidx, ActRef in, float* final_out, long lo
   return BP_OK;
 }
 
+
+// decoder of one chunk on the window-GEMM engine: in_cat (fp32) -> painted tiles
+static int v2_run(bp_net* net, std::vector<V2Op>& ops, float* final_out, long long final_bs, const PostOp& post, int nb,
+                  cudaStream_t s) {
+  V2Plan& P = net->v2;
+  const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
+  for (V2Op& op : ops) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool layer_op = op.index >= 0;
+    if (net->profile && layer_op) {
+      BP_CUDA_TRY(cudaEventCreate(&e0)); BP_CUDA_TRY(cudaEventCreate(&e1));
+      BP_CUDA_TRY(cudaEventRecord(e0, s));
+    }
+    int rc = BP_OK;
+    const ActDesc& in = P.acts[op.in];
+    switch (op.kind) {
+      case V2_TO_NHWC16:
+        rc = launch_nchw32_to_nhwc16(static_cast<const float*>(in.ptr), (long long)in.elems_per_sample(), P.acts[op.out],
+                                     nb, fmt, s);
+        break;
+      case V2_TO_F32: {
+        const ActDesc& o = P.acts[op.out];
+        rc = launch_nhwc16_to_nchw32(in, static_cast<float*>(o.ptr), (long long)o.elems_per_sample(), nb, fmt, s);
+        break;
+      }
+      case V2_WCONV:
+        rc = wconv_launch(op.w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, nb, s);
+        break;
+      case V2_TAIL: {
+        TailParams t = P.tail;
+        if (post.post != POST_NONE) { t.post = 1; t.post_k = post.k; t.post_shift = post.shift; }
+        rc = launch_tail_stencil(static_cast<const float*>(in.ptr), final_out, final_bs, t, post.sigma, in.H, in.W, nb, s);
+        break;
+      }
+      case V2_F32CONV: {
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = static_cast<const float*>(in.ptr); a.in_bs = (long long)in.elems_per_sample();
+        if (op.final) {
+          a.out = final_out; a.out_bs = final_bs;
+          if (post.post != POST_NONE) { a.post = post.post; a.post_sigma = post.sigma; a.post_k = post.k; a.post_shift = post.shift; }
+        } else {
+          a.out = static_cast<float*>(P.acts[op.out].ptr); a.out_bs = (long long)P.acts[op.out].elems_per_sample();
+        }
+        a.nb = nb;
+        if (op.skip >= 0) { a.skip = static_cast<const float*>(P.acts[op.skip].ptr); a.skip_bs = (long long)P.acts[op.skip].elems_per_sample(); }
+        rc = launch_conv_f32(*op.l, a, s);
+        break;
+      }
+    }
+    if (rc != BP_OK) return rc;
+    if (net->profile && layer_op) {
+      BP_CUDA_TRY(cudaEventRecord(e1, s));
+      net->prof_events.emplace_back(e0, e1);
+      net->prof_ids.push_back(op.stack * 1000 + op.index);
+    }
+    if (net->debug && layer_op) {
+      const Layer& l = *op.l;
+      const size_t per = (size_t)l.d.cout * l.OHF * l.OWF;
+      const int nl = (int)net->st[op.stack].layers.size();
+      if (net->dbg[op.stack].size() < (size_t)nl) net->dbg[op.stack].resize(nl, nullptr);
+      float*& dst = net->dbg[op.stack][op.index];
+      if (!dst) BP_CUDA_TRY(cudaMalloc(&dst, sizeof(float) * per * net->chunk));
+      if (op.final) {
+        BP_CUDA_TRY(cudaMemcpy2DAsync(dst, per * sizeof(float), final_out, final_bs * sizeof(float), per * sizeof(float), nb,
+                                      cudaMemcpyDeviceToDevice, s));
+      } else if (P.acts[op.out].f32) {
+        BP_CUDA_TRY(cudaMemcpyAsync(dst, P.acts[op.out].ptr, per * sizeof(float) * nb, cudaMemcpyDeviceToDevice, s));
+      } else {
+        rc = launch_nhwc16_to_nchw32(P.acts[op.out], dst, (long long)per, nb, fmt, s);
+        if (rc != BP_OK) return rc;
+      }
+    }
+  }
+  return BP_OK;
+}
+
 static int upload_params(bp_net* net, const bp_transform_params* tp, int flags, int n, cudaStream_t s) {
   BP_REQUIRE(tp != nullptr && tp->aux != nullptr, BP_E_INVALID, "transform params / aux plane values missing");
   BP_REQUIRE(!(flags & BP_FLAG_TRANSFORM) || tp->sigma_in, BP_E_INVALID, "sigma_in missing");
@@ -454,38 +741,76 @@ static int cvae_chunk_front(bp_net* net, const float* tiles, const bp_transform_
   ActRef in, res;
   const size_t HW = (size_t)net->H * net->W;
   const int mb = net->max_batch;
-  int rc = launch_prepare(tiles + (size_t)c0 * HW, net->in_cat, 3 * (long long)HW, 1, 2, net->params + c0,
-                          net->params + 2 * mb + c0, tp->k_in, tp->shift_in, (flags & BP_FLAG_TRANSFORM) ? 1 : 0,
-                          nb, (int)HW, s);
-  if (rc != BP_OK) return rc;
-  if (need_prior) {
-    PostOp none;
-    in.ptr = net->in_cat + HW; in.bs = 3 * (long long)HW;
-    rc = run_stack(net, ST_PRIOR, in, nullptr, 0, none, nb, s, &res);
+  const int do_t = (flags & BP_FLAG_TRANSFORM) ? 1 : 0;
+  const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
+  V2Plan& P = net->v2;
+  const bool v2_prior = P.built && P.prior_on;
+  const bool need_in_cat = !(P.built && P.front_on) || (need_prior && !v2_prior) || net->debug;
+  int rc;
+  if (need_in_cat) {
+    rc = launch_prepare(tiles + (size_t)c0 * HW, net->in_cat, 3 * (long long)HW, 1, 2, net->params + c0,
+                        net->params + 2 * mb + c0, tp->k_in, tp->shift_in, do_t, nb, (int)HW, s);
     if (rc != BP_OK) return rc;
-    *prior_out = static_cast<float*>(const_cast<void*>(res.ptr));
   }
+  if (!need_prior) return BP_OK;
+  PostOp none;
+  if (v2_prior) {
+    rc = launch_front_prior(tiles + (size_t)c0 * HW, P.acts[P.prior_in], net->params + c0, net->params + 2 * mb + c0,
+                            tp->k_in, tp->shift_in, do_t, nb, fmt, s);
+    if (rc != BP_OK) return rc;
+    rc = v2_run(net, P.prior_ops, nullptr, 0, none, nb, s);
+    if (rc != BP_OK) return rc;
+    *prior_out = static_cast<float*>(P.acts[P.prior_out].ptr);
+    return BP_OK;
+  }
+  in.ptr = net->in_cat + HW; in.bs = 3 * (long long)HW;
+  rc = run_stack(net, ST_PRIOR, in, nullptr, 0, none, nb, s, &res);
+  if (rc != BP_OK) return rc;
+  *prior_out = static_cast<float*>(const_cast<void*>(res.ptr));
   return BP_OK;
 }
 
 // stage B: latent -> painted tile
-static int cvae_chunk_back(bp_net* net, const float* latent, const bp_transform_params* tp, int flags, int c0,
-                           int nb, float* out, cudaStream_t s) {
+static int cvae_chunk_back(bp_net* net, const float* tiles, const float* latent, const bp_transform_params* tp,
+                           int flags, int c0, int nb, float* out, cudaStream_t s) {
   const size_t HW = (size_t)net->H * net->W;
   const size_t lhw = (size_t)net->lh * net->lw;
-  PostOp none;
+  const int mb = net->max_batch;
+  const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
+  PostOp none, post;
+  if (flags & BP_FLAG_INVERSE) {
+    post.post = POST_INV_SHIFT_LOG; post.sigma = net->params + mb + c0;
+    post.k = tp->k_out; post.shift = tp->shift_out;
+  }
   ActRef in, h;
   in.ptr = latent; in.bs = (long long)lhw;
-  int rc = run_stack(net, ST_PZ, in, net->in_cat, 3 * (long long)HW, none, nb, s, nullptr);
-  if (rc != BP_OK) return rc;
+  V2Plan& P = net->v2;
+  int rc;
+  if (!(P.built && P.front_on) || net->debug) {
+    // fp32 p_z_in into channel 0 of in_cat (the fused front kernel has no per-layer outputs to record)
+    rc = run_stack(net, ST_PZ, in, net->in_cat, 3 * (long long)HW, none, nb, s, nullptr);
+    if (rc != BP_OK) return rc;
+  }
+  if (P.built) {
+    if (P.front_on) {
+      rc = launch_front_latent(tiles + (size_t)c0 * HW, latent, P.acts[P.dec_in], net->params + c0,
+                               net->params + 2 * mb + c0, P.pz, tp->k_in, tp->shift_in,
+                               (flags & BP_FLAG_TRANSFORM) ? 1 : 0, net->lh, net->lw, nb, fmt, s);
+      if (rc != BP_OK) return rc;
+      if (net->debug) {
+        // record what the decoder really reads as the last p_z_in tap: channel 0 of the fused kernel's output
+        const int li = (int)net->st[ST_PZ].layers.size() - 1;
+        ActDesc v = P.acts[P.dec_in];
+        v.C = 1;
+        rc = launch_nhwc16_to_nchw32(v, net->dbg[ST_PZ][li], (long long)HW, nb, fmt, s);
+        if (rc != BP_OK) return rc;
+      }
+    }
+    return v2_run(net, P.ops, out, (long long)HW, post, nb, s);
+  }
   in.ptr = net->in_cat; in.bs = 3 * (long long)HW;
   rc = run_stack(net, ST_PYZ, in, nullptr, 0, none, nb, s, &h, net->st[ST_MU].layers[0].tc != nullptr || net->st[ST_MU].layers[0].win != nullptr);
   if (rc != BP_OK) return rc;
-  PostOp post;
-  if (flags & BP_FLAG_INVERSE) {
-    post.post = POST_INV_SHIFT_LOG; post.sigma = net->params + net->max_batch + c0;
-    post.k = tp->k_out; post.shift = tp->shift_out;
-  }
   return run_stack(net, ST_MU, h, out, (long long)HW, post, nb, s, nullptr);
 }
 
@@ -520,7 +845,7 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
       if (rc != BP_OK) return rc;
       lat = net->latent;
     }
-    rc = cvae_chunk_back(net, lat, tp, flags, c0, nb, out + (size_t)c0 * HW, s);
+    rc = cvae_chunk_back(net, tiles, lat, tp, flags, c0, nb, out + (size_t)c0 * HW, s);
     if (rc != BP_OK) return rc;
     if (net->debug) break;  // debug buffers hold one chunk
   }
@@ -760,7 +1085,7 @@ int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transf
       rc = launch_sample_z(net->prior_keep, nullptr, net->latent, nullptr, nullptr, net->min_z_var, nb, (int)lhw,
                            BP_LATENT_SEED, seed, ((uint64_t)d * n + c0) * lhw, s);
       if (rc != BP_OK) return rc;
-      rc = cvae_chunk_back(net, net->latent, tp, flags, c0, nb, net->d_out + (size_t)c0 * HW, s);
+      rc = cvae_chunk_back(net, net->d_in, net->latent, tp, flags, c0, nb, net->d_out + (size_t)c0 * HW, s);
       if (rc != BP_OK) return rc;
       rc = launch_welford(net->d_out + (size_t)c0 * HW, net->var_mean + (size_t)c0 * HW,
                           net->var_m2 + (size_t)c0 * HW, d + 1, HW * nb, s);
@@ -817,7 +1142,7 @@ int bp_net_layer_info(const bp_net* net, int stack, int layer, double* flops, in
   if (flops) *flops = l.flops;
   if (geom) {
     geom[0] = l.d.kind; geom[1] = l.d.cin; geom[2] = l.d.cout; geom[3] = l.d.kernel; geom[4] = l.d.stride;
-    geom[5] = l.H; geom[6] = l.W; geom[7] = l.OHF; geom[8] = l.OWF; geom[9] = l.win ? 2 : (l.tc ? 1 : 0);
+    geom[5] = l.H; geom[6] = l.W; geom[7] = l.OHF; geom[8] = l.OWF; geom[9] = l.v2 ? 3 : (l.win ? 2 : (l.tc ? 1 : 0));
   }
   return BP_OK;
 }

@@ -49,6 +49,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+
+// ---- TMA tiled tensor loads (cuTensorMap descriptors; out-of-bounds box elements are zero-filled) ------
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // ---- cp.async 16 B with zero fill (src_bytes = 0 -> writes 16 zero bytes) -----------------------------
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -108,8 +121,7 @@ __device__ __forceinline__ void umma_f16_pred(uint32_t tmem_d, uint64_t desc_a, 
       "setp.ne.b32 p, %4, 0;\n\t"
       "setp.ne.b32 q, %5, 0;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue));
 }
 __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t issue) {
   asm volatile(
@@ -165,6 +177,23 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // bits [32,46) stride-dimension byte offset >> 4
   d |= (uint64_t)1 << 46;                               // bits [46,48) descriptor version 1 (sm_100)
   // base offset 0, lbo mode 0, bits [61,64) layout type 0 = SWIZZLE_NONE
+  return d;
+}
+
+
+// K-major operand in one of the swizzled canonical layouts: rows of `row_bytes` (32 / 64 / 128) at
+// that pitch, 8-row groups `8*row_bytes` apart, 16-byte chunks XOR-swizzled by the hardware as a
+// function of the shared-memory address bits (so a start address shifted by whole rows stays valid
+// with base_offset = 0 -- verified on B200 by tools/umma_probe.cu).  Layout type field [61,64):
+// 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
+__host__ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, uint32_t row_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                                   // LBO (ignored for swizzled K-major) = 16 B
+  d |= (uint64_t)(((8u * row_bytes) >> 4) & 0x3FFFu) << 32; // SBO = 8 rows
+  d |= (uint64_t)1 << 46;
+  const uint64_t lt = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  d |= lt << 61;
   return d;
 }
 

@@ -1,0 +1,254 @@
+// Lowering of the network's convolution layers to window GEMMs (bp_wconv.h) -- host only.
+//
+//   stride-1 Conv2d (k, p)                   taps (r-p, q-p); G pixels x Jy rows of outputs per M row when
+//                                            the layer is narrow (Toeplitz-expanded weights)
+//   Conv2d with k = 2s, p = s/2 (k4s2p1,     a 2x2-tap stride-1 GEMM over the shifted space-to-depth layout its
+//   k8s4p2)                                  producer writes (block = s x s pixels, s*s*Cin channels)
+//   ConvTranspose2d with k = 2s, p = s/2     s*s sub-pixel phases, each a 2x2-tap GEMM on the input grid; phases
+//                                            are merged into the GEMM N dimension (9 taps, zero-padded weights)
+//                                            while s*s*Cout <= 128
+// Reference modules: baryon_painter/models/utils.py:40-77 (conv_block scale 1/2/4), :128-131.
+#include <algorithm>
+
+#include "bp_wconv.h"
+
+namespace bp {
+
+// stored channels per pixel of a 16-bit NHWC tensor with `c` logical channels
+int v2_padc(int c) { return c <= 4 ? 4 : (c + 7) / 8 * 8; }
+
+static int round_pow2(int v, int lo) {
+  int r = lo;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+// can `l` run as a window GEMM?  *need_b = space-to-depth block of the input layout it reads
+bool v2_eligible(const Layer& l, int* need_b) {
+  const bp_layer_desc& d = l.d;
+  *need_b = 1;
+  if (getenv("BP_V2_OFF")) return false;
+  if (d.cout > 128 || (d.cout & (d.cout - 1)) != 0) return false;
+  if (d.cout < 8 && !(d.cout == 1 && d.kind == BP_CONV && d.stride == 1)) return false;
+  if (d.kind == BP_CONV) {
+    if (d.stride == 1) return d.kernel == 2 * d.pad + 1;   // unit / packing chosen by v2_candidates
+    if (d.kernel != 2 * d.stride || d.pad * 2 != d.stride) return false;
+    if ((d.stride & (d.stride - 1)) != 0) return false;
+    if (l.H % d.stride || l.W % d.stride) return false;
+    const int cs = v2_padc(d.cin) * d.stride * d.stride;
+    if (cs % 16 != 0 || !(cs * 2 <= 128 || (cs * 2) % 128 == 0)) return false;
+    *need_b = d.stride;
+    return true;
+  }
+  // transposed
+  if (d.kernel != 2 * d.stride || d.pad * 2 != d.stride || d.out_pad != 0) return false;
+  return d.cin % 16 == 0 && (d.cin * 2 <= 128 || (d.cin * 2) % 128 == 0);
+}
+
+int v2_make_spec(const Layer& l, int fmt, WSpec* sp) {
+  const bp_layer_desc& d = l.d;
+  const int k = d.kernel, s = d.stride, p = d.pad;
+  const std::vector<float>& w = l.host_weight;
+  const std::vector<float>& sc = l.host_scale;
+  const std::vector<float>& sh = l.host_shift;
+  sp->fmt = fmt;
+  sp->act = d.act;
+  sp->act_param = d.act_param;
+  sp->G = 1; sp->Jy = 1; sp->mode = W_FLAT;
+  const int cout = d.cout, cin = d.cin;
+  const int coutp = round_pow2(cout, 8);
+  if (d.kind == BP_CONV && s == 1) {
+    sp->nphase = 1;
+    sp->OHl = l.OHF; sp->OWl = l.OWF;
+    for (int r = 0; r < k; ++r)
+      for (int q = 0; q < k; ++q) sp->taps[0].push_back({r - p, q - p});
+    sp->N = std::max(16, coutp);
+    sp->seg_len = sp->N; sp->seg_valid = coutp;
+    sp->segs[0].push_back({0, 0});
+    sp->ry = sp->rx = 1;
+    sp->shift.assign(sp->N, 0.f);
+    for (int n = 0; n < cout; ++n) sp->shift[n] = sh[n];
+    sp->weight = [=, &w, &sc](int, int t, int elem, int n) -> float {
+      if (n >= cout || elem >= cin) return 0.f;
+      const int r = t / k, q = t % k;
+      return w[(((size_t)n * cin + elem) * k + r) * k + q] * sc[n];
+    };
+    return BP_OK;
+  }
+  if (d.kind == BP_CONV) {
+    // k = 2s on the shifted space-to-depth input: element = (sy*s + sx)*cin + c
+    sp->nphase = 1;
+    sp->OHl = l.OHF; sp->OWl = l.OWF;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) sp->taps[0].push_back({a, b});
+    sp->N = std::max(16, coutp);
+    sp->seg_len = sp->N; sp->seg_valid = coutp;
+    sp->segs[0].push_back({0, 0});
+    sp->ry = sp->rx = 1;
+    sp->shift.assign(sp->N, 0.f);
+    for (int n = 0; n < cout; ++n) sp->shift[n] = sh[n];
+    sp->weight = [=, &w, &sc](int, int t, int elem, int n) -> float {
+      if (n >= cout) return 0.f;
+      const int a = t / 2, b = t % 2;
+      const int Cp = v2_padc(cin);
+      const int sub = elem / Cp, c = elem % Cp;
+      if (sub >= s * s || c >= cin) return 0.f;
+      const int sy = sub / s, sx = sub % s;
+      return w[(((size_t)n * cin + c) * k + (a * s + sy)) * k + (b * s + sx)] * sc[n];
+    };
+    return BP_OK;
+  }
+  // transposed convolution: phase (ph, pw) of output pixel (s*y + ph, s*x + pw)
+  struct PTap { int dy, dx, r, q; };
+  std::vector<std::vector<PTap>> ptaps(l.nphase);
+  for (int pi = 0; pi < l.nphase; ++pi) {
+    const int ph = l.phase[pi].ph, pw = l.phase[pi].pw;
+    const int r0 = (ph + p) % s, qh = (ph + p) / s, c0 = (pw + p) % s, qw = (pw + p) / s;
+    for (int aa = 0; r0 + s * aa < k; ++aa)
+      for (int bb = 0; c0 + s * bb < k; ++bb) ptaps[pi].push_back({qh - aa, qw - bb, r0 + s * aa, c0 + s * bb});
+  }
+  sp->OHl = l.H; sp->OWl = l.W;
+  sp->ry = sp->rx = s;
+  const bool merge = l.nphase * coutp <= 128 && !getenv("BP_V2_NOMERGE");
+  if (merge) {
+    sp->nphase = 1;
+    std::vector<WTap> all;
+    for (int pi = 0; pi < l.nphase; ++pi)
+      for (const PTap& t : ptaps[pi]) {
+        bool seen = false;
+        for (const WTap& u : all) seen = seen || (u.dl == t.dy && u.du == t.dx);
+        if (!seen) all.push_back({t.dy, t.dx});
+      }
+    std::sort(all.begin(), all.end(), [](const WTap& a, const WTap& b) { return a.dl != b.dl ? a.dl < b.dl : a.du < b.du; });
+    sp->taps[0] = all;
+    sp->N = std::max(16, l.nphase * coutp);
+    sp->seg_len = coutp; sp->seg_valid = coutp;
+    for (int pi = 0; pi < l.nphase; ++pi) sp->segs[0].push_back({l.phase[pi].ph, l.phase[pi].pw});
+    sp->shift.assign(sp->N, 0.f);
+    for (int pi = 0; pi < l.nphase; ++pi)
+      for (int n = 0; n < cout; ++n) sp->shift[pi * coutp + n] = sh[n];
+    const int nph = l.nphase;
+    sp->weight = [=, &w, &sc](int, int t, int elem, int n) -> float {
+      const int pi = n / coutp, co = n % coutp;
+      if (pi >= nph || co >= cout || elem >= cin) return 0.f;
+      for (const PTap& pt : ptaps[pi])
+        if (pt.dy == all[t].dl && pt.dx == all[t].du)
+          return w[(((size_t)elem * cout + co) * k + pt.r) * k + pt.q] * sc[co];
+      return 0.f;
+    };
+    return BP_OK;
+  }
+  sp->nphase = l.nphase;
+  sp->N = std::max(16, coutp);
+  sp->seg_len = sp->N; sp->seg_valid = coutp;
+  sp->shift.assign(sp->N, 0.f);
+  for (int n = 0; n < cout; ++n) sp->shift[n] = sh[n];
+  for (int pi = 0; pi < l.nphase; ++pi) {
+    for (const PTap& t : ptaps[pi]) sp->taps[pi].push_back({t.dy, t.dx});
+    sp->segs[pi].push_back({l.phase[pi].ph, l.phase[pi].pw});
+  }
+  sp->weight = [=, &w, &sc](int pi, int t, int elem, int n) -> float {
+    if (n >= cout || elem >= cin) return 0.f;
+    const PTap& pt = ptaps[pi][t];
+    return w[(((size_t)elem * cout + n) * k + pt.r) * k + pt.q] * sc[n];
+  };
+  return BP_OK;
+}
+
+
+static int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// stride-1 convolution producing a Jy x G pixel block per M row from units of G pixels (Cp stored channels each)
+static int make_spec_packed(const Layer& l, int fmt, int Cp, int G, int Jy, WSpec* sp) {
+  const bp_layer_desc& d = l.d;
+  const int k = d.kernel, p = d.pad, cin = d.cin, cout = d.cout;
+  const std::vector<float>& w = l.host_weight;
+  const std::vector<float>& sc = l.host_scale;
+  const std::vector<float>& sh = l.host_shift;
+  sp->fmt = fmt; sp->act = d.act; sp->act_param = d.act_param;
+  sp->G = G; sp->Jy = Jy;
+  sp->mode = (G == 1 && Jy == 1) ? W_FLAT : W_LINE;
+  sp->nphase = 1;
+  sp->OHl = (l.OHF + Jy - 1) / Jy;
+  sp->OWl = l.OWF / G;
+  for (int dl = -p; dl <= Jy - 1 + p; ++dl)
+    for (int du = floordiv(-p, G); du <= floordiv(G - 1 + p, G); ++du) sp->taps[0].push_back({dl, du});
+  sp->ry = Jy; sp->rx = G;
+  const int coutp = cout == 1 ? 1 : round_pow2(cout, 8);
+  if (cout == 1) {
+    sp->N = std::max(16, Jy * G);
+    sp->seg_len = G; sp->seg_valid = G;
+    for (int jy = 0; jy < Jy; ++jy) sp->segs[0].push_back({jy, 0});
+  } else {
+    sp->N = std::max(16, Jy * G * coutp);
+    sp->seg_len = coutp; sp->seg_valid = coutp;
+    for (int jy = 0; jy < Jy; ++jy)
+      for (int jx = 0; jx < G; ++jx) sp->segs[0].push_back({jy, jx});
+  }
+  sp->shift.assign(sp->N, 0.f);
+  for (int n = 0; n < Jy * G * coutp; ++n)
+    if (n % coutp < cout) sp->shift[n] = sh[n % coutp];
+  std::vector<WTap> taps = sp->taps[0];
+  sp->weight = [=, &w, &sc](int, int t, int elem, int n) -> float {
+    if (n >= Jy * G * coutp) return 0.f;
+    const int co = n % coutp, jx = (n / coutp) % G, jy = n / (coutp * G);
+    const int pp = elem / Cp, c = elem % Cp;
+    if (co >= cout || c >= cin || pp >= G) return 0.f;
+    const int r = taps[t].dl - jy + p, q = taps[t].du * G + pp - jx + p;
+    if (r < 0 || r >= k || q < 0 || q >= k) return 0.f;
+    return w[(((size_t)co * cin + c) * k + r) * k + q] * sc[co];
+  };
+  return BP_OK;
+}
+
+static double mma_cycles(int N) { return std::max(45.5, std::max((4096.0 + 32.0 * N) / 128.0, N / 2.0)); }
+
+// window-GEMM formulations of `l` reading a 16-bit NHWC input with `Cp` stored channels per pixel,
+// cheapest (tensor-pipe issue cycles per output pixel) first; the caller takes the first that fits
+int v2_candidates(const Layer& l, int fmt, int Cp, std::vector<WSpec>* out) {
+  const bp_layer_desc& d = l.d;
+  out->clear();
+  if (!(d.kind == BP_CONV && d.stride == 1)) {
+    WSpec sp;
+    int rc = v2_make_spec(l, fmt, &sp);
+    if (rc != BP_OK) return rc;
+    out->push_back(sp);
+    return BP_OK;
+  }
+  struct Cand { double cost; int G, Jy; };
+  std::vector<Cand> cands;
+  const int coutp = d.cout == 1 ? 1 : round_pow2(d.cout, 8);
+  for (int G : {1, 2, 4, 8}) {
+    const int ub = G * Cp * 2;
+    if (!(ub == 32 || ub == 64 || ub == 128 || (G == 1 && ub % 128 == 0))) continue;
+    if (l.OWF % G) continue;
+    if (d.cout == 1 && G < 4) continue;            // fp32 plane output is written in float4 quads
+    for (int Jy : {1, 2, 4, 8, 16}) {
+      const int N = std::max(16, Jy * G * coutp);
+      if (N > 128) continue;
+      const bool flat = (G == 1 && Jy == 1);
+      const int ntap = (Jy + d.kernel - 1) * (floordiv(G - 1 + d.pad, G) - floordiv(-d.pad, G) + 1);
+      const int kst = std::max(1, ub / 32);
+      const int rows = flat ? 128 : std::min(l.OWF / G, 128);
+      cands.push_back({ntap * kst * mma_cycles(N) / ((double)rows * G * Jy), G, Jy});
+    }
+  }
+  std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.cost < b.cost; });
+  if (const char* e = getenv("BP_V2_PACK")) {       // "cin:cout:k:G:Jy" forces one formulation (tuning aid)
+    int ci, co, kk, g, jy;
+    if (sscanf(e, "%d:%d:%d:%d:%d", &ci, &co, &kk, &g, &jy) == 5 && ci == d.cin && co == d.cout && kk == d.kernel) {
+      cands.clear();
+      cands.push_back({0.0, g, jy});
+    }
+  }
+  for (const Cand& c : cands) {
+    WSpec sp;
+    make_spec_packed(l, fmt, Cp, c.G, c.Jy, &sp);
+    out->push_back(sp);
+  }
+  BP_REQUIRE(!out->empty(), BP_E_UNSUPPORTED, "no window-GEMM formulation for conv %d->%d k%d (Cp=%d)", d.cin, d.cout,
+             d.kernel, Cp);
+  return BP_OK;
+}
+
+}  // namespace bp

@@ -1,0 +1,929 @@
+// Window-GEMM convolution kernel for sm_100a (tcgen05 + TMEM + TMA).  See bp_wconv.h for the
+// lowering; this file holds the kernel, the host-side packing and the layout-conversion kernels.
+//
+// Data movement.  A CTA works on *regions* of T_r M-tiles (128 M rows each).  The input window
+// ("patch") of a region is brought into shared memory ONCE by TMA tiled loads -- box = (unit bytes,
+// PW units, L lines) of the NHWC activation, hardware-swizzled (SWIZZLE_32B/64B/128B by unit size),
+// out-of-image elements zero-filled by the TMA unit, so padding costs nothing.  Units of a patch are
+// rows of the canonical K-major UMMA operand layout; the A tile of filter tap (dl, du) is the same
+// patch seen through a descriptor whose start address is shifted by (dl*PW + du) rows (the swizzle is
+// a function of the shared-memory address, so shifted starts stay valid; tools/umma_probe.cu).
+// Every input element therefore crosses L2->SM once per region instead of once per tap.
+// Weights stream through a ring of 16 KB stages (4 k-steps each) with plain bulk copies.
+//
+// Roles (256 threads, persistent CTAs, one per SM): warp 0 lane 0 = patch TMA producer, warp 1 lane 0 =
+// weight producer, warp 2 = TMEM allocator + single-thread tcgen05.mma issuer, warps 4-7 = epilogue
+// (TMEM -> registers -> +shift (+skip) -> activation -> 16-bit NHWC / fp32 stores) working on the
+// other half of the double-buffered accumulator.
+//
+// Replaces torch.nn.Conv2d / ConvTranspose2d + BatchNorm2d(eval) + activation (+ ResidualBlock add) as
+// built by reference baryon_painter/models/utils.py:22-38, 128-147.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "bp_tc.cuh"
+#include "bp_wconv.h"
+
+namespace bp {
+
+using namespace tc;
+
+constexpr int W_EPI_WARPS = 8;            // epilogue warps (two per TMEM lane quarter, interleaved over column chunks)
+constexpr int W_THREADS = 128 + 32 * W_EPI_WARPS;
+constexpr int W_PSTAGES = 2;
+constexpr int W_BSTAGES = 4;              // barrier slots; a layer uses a.nbst <= 4 weight stages
+constexpr int W_MAX_SEGS = 32;
+constexpr int W_SMEM_LIMIT = 227 * 1024;
+constexpr int W_TABLE_SMEM = 256 * 4 + 256;   // shift table + barriers; + patch stages + weight ring
+
+struct WPhase {
+  int nks, stage_begin, seg_begin;     // k-steps (padded to a multiple of ksb), first weight stage, first segment
+  int dl0, du0, ntl, ntu;              // rectangular tap grid: lines dl0 .. dl0+ntl-1, units du0 .. du0+ntu-1
+};
+
+struct WArgs {
+  int mode, T_r, Jy;
+  int PW, lines, top, left;
+  int Wt, nstrips, regs_per_strip;
+  int OHl, OWl;
+  int ub16;                    // unit block bytes / 16
+  int nkb, kbps, nblk;
+  uint32_t kb_bytes, stage_bytes, box_bytes, bstage_bytes;
+  int ksb, nbst;               // k-steps per weight stage; weight stages
+  int kpu;                     // k-steps per unit block (UB / 32)
+  int nphase, total_segs;
+  WPhase phase[kMaxPhases];
+  int N, seg_shift, seg_valid;
+  int ry, rx;
+  int nb, total_regions;
+  uint32_t tmem_cols;
+  // tables
+  const uint4* wpack;
+  const float* shift;
+  // output: element offset of M row (R, U), segment s = row_base(R, U) + seg_delta[s]
+  void* out;
+  const uint4* skip;
+  int OH, OW, oC, ob;
+  int row_sy, row_sx;          // ob > 1: block strides of the row base (ry / ob, rx / ob), 0 = general (ry = rx = 1)
+  int seg_oy[W_MAX_SEGS], seg_ox[W_MAX_SEGS];
+  long long seg_delta[W_MAX_SEGS];
+  float act_param;
+  int act, fmt;
+  long long* timing;
+  int dbg;                     // BP_V2_DBG experiment bits: 1 no TMEM loads, 2 no stores, 4 no weight copies, 8 no patch copies
+};
+
+template <int ACT>
+__device__ __forceinline__ float w_act(float v, int act, float p) {
+  if (ACT == BP_ACT_NONE) return v;
+  if (ACT == BP_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == BP_ACT_PRELU) return v >= 0.f ? v : v * p;
+  switch (act) {   // generic instantiation
+    case BP_ACT_RELU: return fmaxf(v, 0.f);
+    case BP_ACT_LEAKY:
+    case BP_ACT_PRELU: return v >= 0.f ? v : v * p;
+    case BP_ACT_SOFTPLUS: return v > 20.f ? v : log1pf(expf(v));
+    case BP_ACT_TANH: return tanhf(v);
+    case BP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+// two fp32 -> packed 16-bit pair; fp16 saturates to +-65504 (half2 min/max after the conversion)
+template <int ACT>
+__device__ __forceinline__ uint32_t w_pack16(float a, float b, int fmt) {
+  if (fmt == 0) {
+    __half2 h = __floats2half2_rn(a, b);
+    h = __hmin2(h, __half2half2(__ushort_as_half((unsigned short)0x7BFF)));
+    if (ACT != BP_ACT_RELU) h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0xFBFF)));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 w_unpack16(uint32_t u, int fmt) {
+  if (fmt == 0) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+struct WRegion {
+  int pi, n, strip, rr;
+  int l0;        // M-domain line whose window starts the patch (patch line 0 = input line l0*Jy - top)
+  int tile0;     // patch-local unit offset of M-tile 0
+};
+__device__ __forceinline__ WRegion w_decode(const WArgs& a, int reg) {
+  WRegion R;
+  const int per_img = a.nstrips * a.regs_per_strip;
+  const int per_phase = per_img * a.nb;
+  R.pi = reg / per_phase;
+  int rem = reg - R.pi * per_phase;
+  R.n = rem / per_img;
+  rem -= R.n * per_img;
+  R.strip = rem / a.regs_per_strip;
+  R.rr = rem - R.strip * a.regs_per_strip;
+  if (a.mode == W_LINE) {
+    R.l0 = R.rr * a.T_r;
+    R.tile0 = 0;
+  } else {
+    const int f0 = R.rr * a.T_r * 128;
+    R.l0 = f0 / a.PW;
+    R.tile0 = f0 - R.l0 * a.PW;
+  }
+  return R;
+}
+
+#define W_TWAIT(slot, stmt)                \
+  do {                                     \
+    if (a.timing) {                        \
+      const long long _t0 = clock64();     \
+      stmt;                                \
+      tacc[slot] += clock64() - _t0;       \
+    } else {                               \
+      stmt;                                \
+    }                                      \
+  } while (0)
+
+// ---- MMA issuer (one warp) ---------------------------------------------------------------------------
+// Every lane runs the (warp-uniform) descriptor arithmetic so it stays in uniform registers; one elected
+// lane issues.  Descriptors computed inside `if (lane == 0)` live in vector registers and cost a
+// vector->uniform waterfall per UTCHMMA (130-170 cycles per MMA instead of 64; tools/issue_probe.cu).
+// This warp's instruction stream is the kernel's critical path: T_R is compile-time so the per-slice body
+// is straight-line descriptor increments + MMAs, ring indices are compare-and-reset counters (a runtime
+// modulo would drag the descriptors through the vector ALU), and each ~130-cycle full/empty handshake is
+// amortised over ksb*T_R MMAs.
+template <int T_R>
+__device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB, uint64_t* bars, uint32_t tmem_base,
+                                        long long* tacc) {
+  uint64_t* full_p = bars;
+  uint64_t* empty_p = bars + 2;
+  uint64_t* full_b = bars + 4;
+  uint64_t* empty_b = bars + 8;
+  uint64_t* tfull = bars + 12;
+  uint64_t* tempty = bars + 14;
+  const uint32_t el = elect_one() ? 1u : 0u;
+  const int N = a.N;
+  const uint32_t idesc = make_idesc_f16(a.fmt, N);
+  const uint64_t db_tmpl = make_smem_desc(0, (uint32_t)N * 16u, 128u);
+  const uint64_t da_tmpl = make_smem_desc_sw(0, (uint32_t)a.ub16 * 16u);
+  const uint32_t sB16 = smem_u32(sB) >> 4, sP16 = smem_u32(sP) >> 4;
+  const uint32_t pstage16 = a.stage_bytes >> 4, bstage16 = a.bstage_bytes >> 4, kb16 = a.kb_bytes >> 4;
+  const uint32_t bstep16 = 2u * (uint32_t)N;
+  const uint32_t ub16 = (uint32_t)a.ub16;
+  const uint32_t tile_step16 = (uint32_t)(a.mode == W_LINE ? a.Jy * a.PW : 128) * ub16;
+  const uint32_t line_step = (uint32_t)a.PW * ub16;
+  const int ksb = a.ksb, nbst = a.nbst, nblk = a.nblk, kbps = a.kbps, kpu = a.kpu;
+  const int total_regions = a.total_regions;
+  uint32_t pst = 0, ppar = 0, bst = 0, bpar = 0, as = 0, apar = 0;
+  int kc = 0;
+  uint64_t db = 0;
+
+// one k-step: T_R MMAs sharing the weight slice `db`; handshakes at weight-stage boundaries
+#define W_KSTEP(DA, ACC)                                                                          \
+  do {                                                                                            \
+    if (kc == 0) {                                                                                \
+      W_TWAIT(2, mbar_wait(&full_b[bst], bpar));                                                  \
+      tc_fence_after();                                                                           \
+      db = db_tmpl + (uint64_t)(sB16 + bst * bstage16);                                           \
+    }                                                                                             \
+    _Pragma("unroll") for (int mt = 0; mt < T_R; ++mt)                                            \
+      umma_f16_pred(d_tmem + (uint32_t)(mt * N), (DA) + (uint64_t)((uint32_t)mt * tile_step16), db, idesc, (ACC), el); \
+    db += bstep16;                                                                                \
+    if (++kc == ksb) {                                                                            \
+      umma_commit_pred(&empty_b[bst], el);                                                        \
+      kc = 0;                                                                                     \
+      if (++bst == (uint32_t)nbst) { bst = 0; bpar ^= 1u; }                                       \
+    }                                                                                             \
+  } while (0)
+
+  for (int reg = blockIdx.x; reg < total_regions; reg += gridDim.x) {
+    const WRegion R = w_decode(a, reg);
+    const WPhase P = a.phase[R.pi];
+    W_TWAIT(0, mbar_wait(&tempty[as], apar ^ 1u));
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + as * (uint32_t)(T_R * N);
+    const uint32_t row0 = (uint32_t)((a.top + P.dl0) * a.PW + (a.left + P.du0)) * ub16;
+    int ks = 0;
+    uint32_t acc = 0;
+    for (int blk = 0; blk < nblk; ++blk) {
+      W_TWAIT(1, mbar_wait(&full_p[pst], ppar));
+      tc_fence_after();
+      const uint64_t a_base = da_tmpl + (uint64_t)(sP16 + pst * pstage16 + (uint32_t)R.tile0 * ub16);
+      // k-step order = packing order of the weights: tap line, tap unit, K block of the stage, 32-byte slice
+      if (kbps == 1) {
+        // the units of one tap line are adjacent in the patch: one run of ntu*kpu consecutive 32-byte slices
+        const int run = P.ntu * kpu;
+        uint64_t da_line = a_base + (uint64_t)row0;
+        for (int ti = 0; ti < P.ntl; ++ti, da_line += line_step) {
+          uint64_t da = da_line;
+          for (int sl = 0; sl < run; ++sl, da += 2) {
+            W_KSTEP(da, acc);
+            acc = 1u;
+          }
+        }
+        ks += P.ntl * run;
+      } else {
+        uint32_t o_line = row0;
+        for (int ti = 0; ti < P.ntl; ++ti, o_line += line_step) {
+          uint32_t o_unit = o_line;
+          for (int tj = 0; tj < P.ntu; ++tj, o_unit += ub16) {
+            uint32_t o = o_unit;
+            for (int j = 0; j < kbps; ++j, o += kb16) {
+              uint64_t da = a_base + (uint64_t)o;
+              for (int k4 = 0; k4 < kpu; ++k4, da += 2) {
+                W_KSTEP(da, acc);
+                acc = 1u;
+              }
+            }
+          }
+        }
+        ks += P.ntl * P.ntu * kbps * kpu;
+      }
+      if (blk == nblk - 1) {
+        // zero-weight padding up to a whole weight stage (any valid A address)
+        for (; ks < P.nks; ++ks) W_KSTEP(a_base, 1u);
+      }
+      umma_commit_pred(&empty_p[pst], el);
+      if (++pst == 2u) { pst = 0; ppar ^= 1u; }
+    }
+    umma_commit_pred(&tfull[as], el);
+    if (++as == 2u) { as = 0; apar ^= 1u; }
+  }
+#undef W_KSTEP
+}
+
+template <int ACT, bool SKIP, bool OUTF32>
+__global__ void __launch_bounds__(W_THREADS, 1)
+wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sP = smem;
+  uint8_t* sB = smem + W_PSTAGES * a.stage_bytes;
+  float* s_shift = reinterpret_cast<float*>(sB + a.nbst * a.bstage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* full_p = bars;             // [2] expect_tx arrival + TMA bytes
+  uint64_t* empty_p = bars + 2;        // [2] MMA commit
+  uint64_t* full_b = bars + 4;         // [4]
+  uint64_t* empty_b = bars + 8;        // [4]
+  uint64_t* tfull = bars + 12;         // [2] MMA commit
+  uint64_t* tempty = bars + 14;        // [2] epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N;
+  long long tacc[3] = {0, 0, 0};
+  const long long t_start = a.timing ? clock64() : 0;
+
+  for (int i = tid; i < N; i += W_THREADS) s_shift[i] = a.shift[i];
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_p[s], 1);
+      mbar_init(&empty_p[s], 1);
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 32 * W_EPI_WARPS);
+    }
+    for (int s = 0; s < W_BSTAGES; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, a.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== patch producer =====================
+    if (lane == 0) {
+      uint32_t pit = 0;
+      for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x) {
+        const WRegion R = w_decode(a, reg);
+        const int u0 = R.strip * a.Wt - a.left;
+        const int y0 = R.l0 * a.Jy - a.top;
+        for (int blk = 0; blk < a.nblk; ++blk, ++pit) {
+          const uint32_t st = pit & 1u, par = (pit >> 1) & 1u;
+          W_TWAIT(0, mbar_wait(&empty_p[st], par ^ 1u));
+          if (a.dbg & 8) { mbar_arrive(&full_p[st]); continue; }
+          mbar_arrive_expect_tx(&full_p[st], a.box_bytes * (uint32_t)a.kbps);
+          for (int j = 0; j < a.kbps; ++j)
+            tma_load_5d(sP + st * a.stage_bytes + j * a.kb_bytes, &tmap, 0, blk * a.kbps + j, u0, y0, R.n, &full_p[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      const uint32_t b_bytes = (uint32_t)N * 32u * (uint32_t)a.ksb;
+      uint32_t st = 0, par = 0;
+      for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x) {
+        const WRegion R = w_decode(a, reg);
+        const WPhase P = a.phase[R.pi];
+        const int nst = P.nks / a.ksb;
+        for (int sg = 0; sg < nst; ++sg) {
+          W_TWAIT(0, mbar_wait(&empty_b[st], par ^ 1u));
+          if (a.dbg & 4) {
+            mbar_arrive(&full_b[st]);
+          } else {
+            mbar_arrive_expect_tx(&full_b[st], b_bytes);
+            bulk_g2s(sB + st * a.bstage_bytes, a.wpack + (size_t)(P.stage_begin + sg) * (size_t)(a.ksb * 2 * N), b_bytes,
+                     &full_b[st]);
+          }
+          if (++st == (uint32_t)a.nbst) { st = 0; par ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    switch (a.T_r) {
+      case 1: w_issue<1>(a, sP, sB, bars, tmem_base, tacc); break;
+      case 2: w_issue<2>(a, sP, sB, bars, tmem_base, tacc); break;
+      case 3: w_issue<3>(a, sP, sB, bars, tmem_base, tacc); break;
+      default: w_issue<4>(a, sP, sB, bars, tmem_base, tacc); break;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    // warp = 4 + e: TMEM lane quarter e % 4 (a warp may only touch lanes 32*(warp % 4) ..), 16-column chunks
+    // e / 4, e / 4 + W_EPI_WARPS / 4, ...  One thread = one M row; a chunk's two 8-column halves are 16-byte
+    // stores to row_base + seg_delta[segment] (+ channel).
+    constexpr int NEW = W_EPI_WARPS / 4;
+    const int q = warp & 3;
+    const int cpart = (warp - 4) >> 2;
+    const int m = q * 32 + lane;
+    const int seg_mask = (1 << a.seg_shift) - 1;
+    const int ob = a.ob;
+    uint32_t as = 0, apar = 0;
+    for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x) {
+      const WRegion R = w_decode(a, reg);
+      const WPhase P = a.phase[R.pi];
+      bool waited = false;
+      for (int mt = 0; mt < a.T_r; ++mt) {
+        int Rl, c;
+        if (a.mode == W_LINE) {
+          Rl = R.l0 + mt;
+          c = m;
+        } else {
+          const int f = R.rr * a.T_r * 128 + mt * 128 + m;
+          Rl = f / a.PW;
+          c = f - Rl * a.PW;
+        }
+        const int U = R.strip * a.Wt + c;
+        const bool valid = c < a.Wt && U < a.OWl && Rl < a.OHl;
+        // element offset of this row's block and whether any of its pixels can fall outside the image
+        const int y0 = Rl * a.ry, x0 = U * a.rx;
+        long long rbase;
+        if (ob == 1) {
+          rbase = (((long long)R.n * a.OH + y0) * a.OW + x0) * a.oC;
+        } else {
+          const int Hs = a.OH / ob + 1, Ws = a.OW / ob + 1;
+          if (a.row_sy) {
+            rbase = ((((long long)R.n * Hs + (long long)Rl * a.row_sy) * Ws + (long long)U * a.row_sx) * ob * ob) * a.oC;
+          } else {
+            const int yy = y0 + (ob >> 1), xx = x0 + (ob >> 1);
+            const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
+            rbase = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * a.oC;
+          }
+        }
+        const bool edge = (y0 + a.ry > a.OH) || (x0 + a.rx > a.OW);
+        // residual input of this row (same NHWC position as the output): fetched two chunks ahead of use
+        const uint4* sp = nullptr;
+        uint4 sk0[2], sk1[2], sk2[2];
+        if (SKIP) {
+          sp = a.skip + (rbase >> 3) + cpart * 2;
+          if (valid) {
+            sk0[0] = __ldg(sp); sk0[1] = __ldg(sp + 1);
+            if (N > 16 * NEW) { sk1[0] = __ldg(sp + 2 * NEW); sk1[1] = __ldg(sp + 2 * NEW + 1); }
+          }
+        }
+        if (!waited) {
+          W_TWAIT(0, mbar_wait(&tfull[as], apar));
+          tc_fence_after();
+          waited = true;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(a.T_r * N) + (uint32_t)(mt * N);
+#pragma unroll 1
+        for (int c0 = cpart * 16; c0 < N; c0 += 16 * NEW) {
+          if (SKIP && valid && c0 + 32 * NEW < N) {
+            sk2[0] = __ldg(sp + (c0 >> 3) + 4 * NEW - cpart * 2);
+            sk2[1] = __ldg(sp + (c0 >> 3) + 4 * NEW - cpart * 2 + 1);
+          }
+          uint32_t v[16];
+          if (a.dbg & 1) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0u;
+          } else {
+            tmem_ld16(taddr + (uint32_t)c0, v);
+            tmem_ld_wait();
+          }
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
+          if (OUTF32) {
+            // fp32 output (single channel plane): segments of >= 4 columns, one float4 per quad
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int n0 = c0 + h * 4;
+              const int seg = P.seg_begin + (n0 >> a.seg_shift), ch = n0 & seg_mask;
+              if (ch >= a.seg_valid) continue;                          // warp-uniform
+              if (!valid || (a.dbg & 2)) continue;
+              if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
+              float* o = reinterpret_cast<float*>(a.out) + (rbase + a.seg_delta[seg] + ch);
+              const float4 s4 = sh4[h];
+              float4 r;
+              r.x = w_act<ACT>(__uint_as_float(v[h * 4 + 0]) + s4.x, a.act, a.act_param);
+              r.y = w_act<ACT>(__uint_as_float(v[h * 4 + 1]) + s4.y, a.act, a.act_param);
+              r.z = w_act<ACT>(__uint_as_float(v[h * 4 + 2]) + s4.z, a.act, a.act_param);
+              r.w = w_act<ACT>(__uint_as_float(v[h * 4 + 3]) + s4.w, a.act, a.act_param);
+              if (a.seg_valid - ch >= 4) {
+                *reinterpret_cast<float4*>(o) = r;
+              } else {
+                if (ch + 0 < a.seg_valid) o[0] = r.x;
+                if (ch + 1 < a.seg_valid) o[1] = r.y;
+                if (ch + 2 < a.seg_valid) o[2] = r.z;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int n0 = c0 + h * 8;
+              const int seg = P.seg_begin + (n0 >> a.seg_shift), ch = n0 & seg_mask;
+              if (ch >= a.seg_valid) continue;                          // warp-uniform
+              if (!valid || (a.dbg & 2)) continue;
+              if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
+              const float4 sa = sh4[h * 2], sb = sh4[h * 2 + 1];
+              float xv[8];
+              xv[0] = __uint_as_float(v[h * 8 + 0]) + sa.x; xv[1] = __uint_as_float(v[h * 8 + 1]) + sa.y;
+              xv[2] = __uint_as_float(v[h * 8 + 2]) + sa.z; xv[3] = __uint_as_float(v[h * 8 + 3]) + sa.w;
+              xv[4] = __uint_as_float(v[h * 8 + 4]) + sb.x; xv[5] = __uint_as_float(v[h * 8 + 5]) + sb.y;
+              xv[6] = __uint_as_float(v[h * 8 + 6]) + sb.z; xv[7] = __uint_as_float(v[h * 8 + 7]) + sb.w;
+              if (SKIP) {
+                const uint4 s4 = sk0[h];
+                const float2 s0 = w_unpack16(s4.x, a.fmt), s1 = w_unpack16(s4.y, a.fmt), s2 = w_unpack16(s4.z, a.fmt),
+                             s3 = w_unpack16(s4.w, a.fmt);
+                xv[0] += s0.x; xv[1] += s0.y; xv[2] += s1.x; xv[3] += s1.y;
+                xv[4] += s2.x; xv[5] += s2.y; xv[6] += s3.x; xv[7] += s3.y;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) xv[e] = w_act<ACT>(xv[e], a.act, a.act_param);
+              uint4 o;
+              o.x = w_pack16<ACT>(xv[0], xv[1], a.fmt); o.y = w_pack16<ACT>(xv[2], xv[3], a.fmt);
+              o.z = w_pack16<ACT>(xv[4], xv[5], a.fmt); o.w = w_pack16<ACT>(xv[6], xv[7], a.fmt);
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + (rbase + a.seg_delta[seg] + ch)) = o;
+            }
+          }
+          if (SKIP) {
+            sk0[0] = sk1[0]; sk0[1] = sk1[1];
+            sk1[0] = sk2[0]; sk1[1] = sk2[1];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      if (++as == 2u) { as = 0; apar ^= 1u; }
+    }
+  }
+  if (a.timing && lane == 0) {
+    // per CTA: [0] total, [1] patch producer wait, [2] weight producer wait, [3..5] MMA waits on
+    // tempty / full_p / full_b, [6] epilogue (warp 4) wait on tfull
+    long long* t = a.timing + (size_t)blockIdx.x * 8;
+    if (warp == 0) { t[0] = clock64() - t_start; t[1] = tacc[0]; }
+    if (warp == 1) t[2] = tacc[0];
+    if (warp == 2) { t[3] = tacc[0]; t[4] = tacc[1]; t[5] = tacc[2]; }
+    if (warp == 4) t[6] = tacc[0];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+struct WLayer {
+  WArgs proto;
+  CUtensorMap tmap;
+  uint4* wpack = nullptr;
+  float* shift = nullptr;
+  std::vector<int2> segs;          // (oy, ox) per segment, phases concatenated
+  size_t smem = 0;
+  long long mmas_per_region[kMaxPhases];
+  int act = 0;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static uint16_t w_to16(float v, int fmt) {
+  uint16_t u;
+  if (fmt == 0) {
+    __half h = __float2half_rn(v);
+    memcpy(&u, &h, 2);
+  } else {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    memcpy(&u, &h, 2);
+  }
+  return u;
+}
+
+static double w_mma_floor(int N) { return std::max(45.5, std::max((4096.0 + 32.0 * N) / 128.0, N / 2.0)); }
+
+int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
+  *out = nullptr;
+  BP_REQUIRE(!in.f32 && in.ptr, BP_E_INVALID, "window GEMM input must be a 16-bit NHWC tensor");
+  const int Cs = in.b * in.b * in.Cp;                 // stored channels per stored pixel
+  const int Hs = in.Hs(), Ws = in.Ws();
+  BP_REQUIRE(Ws % sp.G == 0 || sp.G == 1, BP_E_UNSUPPORTED, "window GEMM: line width %d not a multiple of G=%d", Ws,
+             sp.G);
+  const int unit_bytes = sp.G * Cs * 2;
+  int UB, nkb;
+  if (unit_bytes <= 128) {
+    UB = unit_bytes; nkb = 1;
+    BP_REQUIRE(UB == 32 || UB == 64 || UB == 128, BP_E_UNSUPPORTED, "window GEMM: unit of %d bytes", UB);
+  } else {
+    UB = 128; nkb = unit_bytes / 128;
+    BP_REQUIRE(unit_bytes % 128 == 0, BP_E_UNSUPPORTED, "window GEMM: unit of %d bytes", unit_bytes);
+  }
+  BP_REQUIRE(sp.N >= 16 && sp.N <= 256 && sp.N % 16 == 0, BP_E_UNSUPPORTED, "window GEMM: N=%d", sp.N);
+  BP_REQUIRE((sp.seg_len & (sp.seg_len - 1)) == 0 && sp.seg_len >= 4, BP_E_UNSUPPORTED, "segment length %d", sp.seg_len);
+  const int kpu = UB / 32;
+
+  // ---- tap grids: every phase's taps must form a full rectangle (true for all lowerings in bp_v2.cu)
+  struct Grid { int dl0, du0, ntl, ntu; std::vector<int> index; };
+  std::vector<Grid> grids(sp.nphase);
+  int dl_min = 0, dl_max = 0, du_min = 0, du_max = 0;
+  int max_taps = 0;
+  for (int pi = 0; pi < sp.nphase; ++pi) {
+    Grid& g = grids[pi];
+    BP_REQUIRE(!sp.taps[pi].empty(), BP_E_INVALID, "window GEMM: phase without taps");
+    int l0 = 1 << 30, l1 = -(1 << 30), u0 = 1 << 30, u1 = -(1 << 30);
+    for (const WTap& t : sp.taps[pi]) {
+      l0 = std::min(l0, t.dl); l1 = std::max(l1, t.dl);
+      u0 = std::min(u0, t.du); u1 = std::max(u1, t.du);
+    }
+    g.dl0 = l0; g.du0 = u0; g.ntl = l1 - l0 + 1; g.ntu = u1 - u0 + 1;
+    g.index.assign((size_t)g.ntl * g.ntu, -1);
+    for (size_t t = 0; t < sp.taps[pi].size(); ++t)
+      g.index[(size_t)(sp.taps[pi][t].dl - l0) * g.ntu + (sp.taps[pi][t].du - u0)] = (int)t;
+    for (int v : g.index) BP_REQUIRE(v >= 0, BP_E_UNSUPPORTED, "window GEMM: taps of phase %d are not a rectangle", pi);
+    dl_min = std::min(dl_min, l0); dl_max = std::max(dl_max, l1);
+    du_min = std::min(du_min, u0); du_max = std::max(du_max, u1);
+    max_taps = std::max(max_taps, g.ntl * g.ntu);
+  }
+
+  WLayer* wl = new WLayer();
+  WArgs& a = wl->proto;
+  memset(&a, 0, sizeof(a));
+  wl->act = sp.act;
+  a.mode = sp.mode; a.Jy = sp.Jy;
+  a.OHl = sp.OHl; a.OWl = sp.OWl;
+  a.ub16 = UB / 16; a.nkb = nkb; a.kpu = kpu;
+  a.N = sp.N; a.seg_valid = sp.seg_valid; a.ry = sp.ry; a.rx = sp.rx;
+  a.seg_shift = 0;
+  while ((1 << a.seg_shift) < sp.seg_len) ++a.seg_shift;
+  a.act = sp.act; a.act_param = sp.act_param; a.fmt = sp.fmt;
+  a.nphase = sp.nphase;
+  a.top = -dl_min; a.left = -du_min;
+  const int bottom = dl_max - (sp.Jy - 1) > 0 ? dl_max - (sp.Jy - 1) : 0;   // lines below the block's last own line
+  const int right = du_max;
+
+  // ---- tiling search: strip width, M-tiles per region, K blocks per patch stage, weight-stage depth.
+  // Score = tensor-pipe cycles per useful M row: MMA floor + the ~130-cycle stage handshake amortised over
+  // the stage's MMAs, inflated by the discarded halo columns of the flat domain and by weight rings too
+  // shallow to cover the L2 latency.
+  struct Choice { double score; int Wt, T_r, kbps, ksb, nbst; };
+  Choice best{1e30, 0, 0, 0, 0, 0};
+  std::vector<int> wts;
+  if (sp.mode == W_LINE) {
+    wts.push_back(std::min(sp.OWl, 128));
+  } else {
+    if (sp.OWl + a.left + right <= 256) wts.push_back(sp.OWl);
+    for (int w : {128, 64})
+      if (w < sp.OWl) wts.push_back(w);
+  }
+  for (int Wt : wts) {
+    const int PW = Wt + a.left + right;
+    if (PW > 256) continue;
+    for (int T_r = std::max(1, std::min(4, 256 / sp.N)); T_r >= 1; --T_r) {
+      const int lines = sp.mode == W_LINE ? T_r * sp.Jy + a.top + bottom : (T_r * 128 + PW - 1) / PW + 1 + a.top + bottom;
+      if (lines > 256) continue;
+      const size_t box = (size_t)UB * PW * lines;
+      const size_t kb_bytes = (box + (size_t)UB * (a.left + right + 8) + 1023) / 1024 * 1024;
+      for (int kbps = nkb; kbps >= 1; kbps /= 2) {
+        if (nkb % kbps) continue;
+        for (int ksb : {16, 12, 8, 6, 4}) {
+          const size_t bstage = (size_t)sp.N * 32 * ksb;
+          if (bstage > 49152) continue;
+          for (int nbst : {4, 3, 2}) {
+            const size_t smem = W_PSTAGES * kb_bytes * kbps + nbst * bstage + W_TABLE_SMEM;
+            if (smem > (size_t)W_SMEM_LIMIT) continue;
+            const double fl = w_mma_floor(sp.N);
+            double cyc = fl + 130.0 / (ksb * T_r);
+            // padding of the k-step count to whole stages
+            double pad = 0;
+            for (const Grid& g : grids) {
+              const int real = g.ntl * g.ntu * nkb * kpu;
+              pad += (double)((real + ksb - 1) / ksb * ksb) / real;
+            }
+            cyc *= pad / grids.size();
+            if (sp.mode == W_FLAT) cyc *= (double)PW / Wt;
+            const double buffered = (double)nbst * ksb * T_r * fl;
+            if (buffered < 2500.0) cyc *= 1.0 + 0.15 * (2500.0 - buffered) / 2500.0;
+            cyc += 400.0 / (T_r * max_taps * nkb * kpu);          // per-region handshakes
+            if (cyc < best.score) best = Choice{cyc, Wt, T_r, kbps, ksb, nbst};
+          }
+        }
+      }
+    }
+  }
+  if (best.Wt == 0) {
+    delete wl;
+    set_error("window GEMM: no tiling of a %d-byte x %d-block unit window fits in shared memory", UB, nkb);
+    return BP_E_UNSUPPORTED;
+  }
+  a.Wt = best.Wt; a.T_r = best.T_r; a.kbps = best.kbps; a.ksb = best.ksb; a.nbst = best.nbst;
+  a.PW = a.Wt + a.left + right;
+  a.nstrips = (sp.OWl + a.Wt - 1) / a.Wt;
+  if (sp.mode == W_LINE) a.lines = a.T_r * sp.Jy + a.top + bottom;
+  else a.lines = (a.T_r * 128 + a.PW - 1) / a.PW + 1 + a.top + bottom;
+  a.box_bytes = (uint32_t)UB * a.PW * a.lines;
+  // slack: garbage M rows of the last tile read up to (left + right) units past the box
+  a.kb_bytes = (uint32_t)(((size_t)a.box_bytes + (size_t)UB * (a.left + right + 8) + 1023) / 1024 * 1024);
+  a.stage_bytes = a.kb_bytes * a.kbps;
+  a.bstage_bytes = (uint32_t)sp.N * 32u * (uint32_t)a.ksb;
+  a.nblk = nkb / a.kbps;
+  if (sp.mode == W_LINE) a.regs_per_strip = (sp.OHl + a.T_r - 1) / a.T_r;
+  else a.regs_per_strip = (sp.OHl * a.PW + a.T_r * 128 - 1) / (a.T_r * 128);
+  uint32_t cols = 32;
+  while (cols < 2u * (uint32_t)(a.T_r * a.N)) cols <<= 1;
+  BP_REQUIRE(cols <= 512, BP_E_UNSUPPORTED, "window GEMM: accumulators exceed TMEM");
+  a.tmem_cols = cols;
+
+  // ---- packed weights (k-step order = the MMA issuer's loop nest: block, tap line, tap unit, K block, slice)
+  std::vector<uint16_t> wp;
+  std::vector<int2> segs;
+  int stage_total = 0;
+  for (int pi = 0; pi < sp.nphase; ++pi) {
+    WPhase& P = a.phase[pi];
+    const Grid& g = grids[pi];
+    P.dl0 = g.dl0; P.du0 = g.du0; P.ntl = g.ntl; P.ntu = g.ntu;
+    P.stage_begin = stage_total;
+    P.seg_begin = (int)segs.size();
+    for (const WSegOff& sg : sp.segs[pi]) segs.push_back(make_int2(sg.oy, sg.ox));
+    const int ntaps = g.ntl * g.ntu;
+    const int real = ntaps * nkb * kpu;
+    P.nks = (real + a.ksb - 1) / a.ksb * a.ksb;
+    wp.resize((size_t)(stage_total + P.nks / a.ksb) * a.ksb * 2 * a.N * 8, 0);
+    int ks = 0;
+    for (int blk = 0; blk < a.nblk; ++blk)
+      for (int t = 0; t < ntaps; ++t)
+        for (int j = 0; j < a.kbps; ++j)
+          for (int k4 = 0; k4 < kpu; ++k4, ++ks) {
+            const int kb = blk * a.kbps + j;
+            const int stage = stage_total + ks / a.ksb, kin = ks % a.ksb;
+            for (int half = 0; half < 2; ++half)
+              for (int n = 0; n < a.N; ++n)
+                for (int e = 0; e < 8; ++e) {
+                  const int elem = kb * (UB / 2) + k4 * 16 + half * 8 + e;
+                  const float w = sp.weight(pi, g.index[t], elem, n);
+                  if (w != 0.f) wp[((((size_t)stage * a.ksb + kin) * 2 + half) * a.N + n) * 8 + e] = w_to16(w, sp.fmt);
+                }
+          }
+    stage_total += P.nks / a.ksb;
+    wl->mmas_per_region[pi] = (long long)P.nks * a.T_r;
+  }
+  a.total_segs = (int)segs.size();
+  if (a.total_segs > W_MAX_SEGS) {
+    delete wl;
+    set_error("window GEMM: %d segments exceed the table", a.total_segs);
+    return BP_E_UNSUPPORTED;
+  }
+  wl->smem = W_PSTAGES * (size_t)a.stage_bytes + (size_t)a.nbst * a.bstage_bytes + W_TABLE_SMEM;
+
+  // ---- TMA tensor map: (elements of a unit block, K blocks, units, lines, samples)
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    delete wl;
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return BP_E_CUDA;
+  }
+  const cuuint64_t Wu = (cuuint64_t)(Ws / sp.G);
+  const cuuint64_t gdim[5] = {(cuuint64_t)(UB / 2), (cuuint64_t)nkb, Wu, (cuuint64_t)Hs, (cuuint64_t)nb_max};
+  const cuuint64_t gstr[4] = {(cuuint64_t)UB, (cuuint64_t)unit_bytes, (cuuint64_t)Ws * Cs * 2,
+                              (cuuint64_t)Hs * Ws * Cs * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)(UB / 2), 1u, (cuuint32_t)a.PW, (cuuint32_t)a.lines, 1u};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle swz = UB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                           : (UB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(&wl->tmap, sp.fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                   in.ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    delete wl;
+    set_error("cuTensorMapEncodeTiled failed (%d): unit %d B x %d blocks, %llu units, %d lines, box %d x %d", (int)r, UB,
+              nkb, (unsigned long long)Wu, Hs, a.PW, a.lines);
+    return BP_E_CUDA;
+  }
+
+  std::vector<float> shift(a.N, 0.f);
+  for (int n = 0; n < a.N && n < (int)sp.shift.size(); ++n) shift[n] = sp.shift[n];
+  if (segs.empty()) segs.push_back(make_int2(0, 0));
+  wl->segs = segs;
+  BP_CUDA_TRY(cudaMalloc(&wl->wpack, wp.size() * sizeof(uint16_t)));
+  BP_CUDA_TRY(cudaMalloc(&wl->shift, shift.size() * sizeof(float)));
+  BP_CUDA_TRY(cudaMemcpy(wl->wpack, wp.data(), wp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  BP_CUDA_TRY(cudaMemcpy(wl->shift, shift.data(), shift.size() * sizeof(float), cudaMemcpyHostToDevice));
+  a.wpack = wl->wpack; a.shift = wl->shift;
+  *out = wl;
+  return BP_OK;
+}
+
+void wconv_free(WLayer* w) {
+  if (!w) return;
+  cudaFree(w->wpack); cudaFree(w->shift);
+  delete w;
+}
+
+typedef void (*WKernel)(const CUtensorMap, const WArgs);
+
+// instantiated variants: ReLU (+ residual), PReLU (16-bit / fp32 plane), generic activation switch
+static WKernel pick_kernel(int act, bool skip, bool f32) {
+  if (act == BP_ACT_RELU && !f32) return skip ? wconv_kernel<BP_ACT_RELU, true, false> : wconv_kernel<BP_ACT_RELU, false, false>;
+  if ((act == BP_ACT_PRELU || act == BP_ACT_LEAKY) && !skip)
+    return f32 ? wconv_kernel<BP_ACT_PRELU, false, true> : wconv_kernel<BP_ACT_PRELU, false, false>;
+  if (skip) return f32 ? nullptr : wconv_kernel<-1, true, false>;
+  return f32 ? wconv_kernel<-1, false, true> : wconv_kernel<-1, false, false>;
+}
+
+static int g_w_sms = 0;
+
+int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb, cudaStream_t s) {
+  BP_REQUIRE(wl && out.ptr, BP_E_INVALID, "window GEMM: null layer / output");
+  if (g_w_sms == 0) {
+    int dev = 0;
+    BP_CUDA_TRY(cudaGetDevice(&dev));
+    BP_CUDA_TRY(cudaDeviceGetAttribute(&g_w_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  WArgs a = wl->proto;
+  a.out = out.ptr;
+  a.skip = static_cast<const uint4*>(skip);
+  a.OH = out.H; a.OW = out.W; a.ob = out.b;
+  a.oC = out.f32 ? 1 : out.Cp;
+  BP_REQUIRE(!out.f32 || out.C == 1, BP_E_UNSUPPORTED, "window GEMM: fp32 output with %d channels", out.C);
+  BP_REQUIRE(!skip || (out.b == 1 && !out.f32 && a.N <= 128 && a.ry == 1 && a.rx == 1), BP_E_UNSUPPORTED,
+             "window GEMM: residual add on this output layout");
+  a.nb = nb;
+  a.total_regions = a.nphase * nb * a.nstrips * a.regs_per_strip;
+  // per-segment element offsets relative to the row base (see the epilogue)
+  {
+    const int b = out.b, pd = b >> 1;
+    a.row_sy = a.row_sx = 0;
+    if (b > 1 && !(a.ry == 1 && a.rx == 1)) {
+      BP_REQUIRE(a.ry % b == 0 && a.rx % b == 0 && !out.f32, BP_E_UNSUPPORTED,
+                 "window GEMM: %dx%d output blocks into a space-to-depth %d layout", a.ry, a.rx, b);
+      a.row_sy = a.ry / b; a.row_sx = a.rx / b;
+    }
+    const long long Ws = out.Ws();
+    for (size_t i = 0; i < wl->segs.size(); ++i) {
+      const int oy = wl->segs[i].x, ox = wl->segs[i].y;
+      a.seg_oy[i] = oy; a.seg_ox[i] = ox;
+      if (b == 1) a.seg_delta[i] = ((long long)oy * out.W + ox) * a.oC;
+      else if (a.row_sy) a.seg_delta[i] = (((long long)((oy + pd) / b) * Ws + (ox + pd) / b) * b * b + ((oy + pd) % b) * b + (ox + pd) % b) * a.oC;
+      else a.seg_delta[i] = 0;
+    }
+    if (b > 1 && !a.row_sy) BP_REQUIRE(wl->segs.size() == 1 && wl->segs[0].x == 0 && wl->segs[0].y == 0, BP_E_UNSUPPORTED,
+                                     "window GEMM: segmented output into a space-to-depth layout");
+  }
+  const int grid = std::min(a.total_regions, g_w_sms);
+  WKernel k = pick_kernel(wl->act, skip != nullptr, out.f32);
+  BP_REQUIRE(k != nullptr, BP_E_UNSUPPORTED, "window GEMM: residual add with fp32 output");
+  static const int dbg = getenv("BP_V2_DBG") ? atoi(getenv("BP_V2_DBG")) : 0;
+  a.dbg = dbg;
+  static const bool timing = getenv("BP_WIN_TIMING") != nullptr;
+  static long long* d_timing = nullptr;
+  if (timing) {
+    if (!d_timing) BP_CUDA_TRY(cudaMalloc(&d_timing, sizeof(long long) * 8 * 256));
+    BP_CUDA_TRY(cudaMemsetAsync(d_timing, 0, sizeof(long long) * 8 * 256, s));
+    a.timing = d_timing;
+  }
+  BP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_LIMIT));
+  k<<<grid, W_THREADS, wl->smem, s>>>(wl->tmap, a);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  if (timing) {
+    BP_CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<long long> h(8 * 256);
+    BP_CUDA_TRY(cudaMemcpy(h.data(), d_timing, sizeof(long long) * 8 * 256, cudaMemcpyDeviceToHost));
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < grid; ++c)
+      for (int q = 0; q < 7; ++q) acc[q] += (double)h[c * 8 + q] / grid;
+    double floor_cyc = 0;
+    const long long mm = wconv_mma_count(wl, nb, &floor_cyc);
+    fprintf(stderr,
+            "[wconv] N=%d T_r=%d ksb=%d nbst=%d mode=%d ub=%d nkb=%d/%d PW=%d lines=%d regions/cta=%.1f mma/cta=%.0f floor=%.0f total=%.0f cyc"
+            " | waits: A-prod %.0f B-prod %.0f mma:tempty %.0f mma:full_p %.0f mma:full_b %.0f epi:tfull %.0f\n",
+            a.N, a.T_r, a.ksb, a.nbst, a.mode, a.ub16 * 16, a.nkb, a.kbps, a.PW, a.lines, (double)a.total_regions / grid, (double)mm / grid,
+            floor_cyc / grid, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
+  }
+  return BP_OK;
+}
+
+// tcgen05.mma instructions of one launch and their issue floor in SM cycles (measured: max(45.5,
+// (4096 + 32 N)/128, N/2) cycles per M=128, K=16 instruction with both operands in shared memory)
+int wconv_mma_count(const WLayer* wl, int nb, double* cycles_floor) {
+  const WArgs& a = wl->proto;
+  long long mm = 0;
+  for (int pi = 0; pi < a.nphase; ++pi) mm += wl->mmas_per_region[pi] * (long long)nb * a.nstrips * a.regs_per_strip;
+  const double per = w_mma_floor(a.N);
+  if (cycles_floor) *cycles_floor = (double)mm * per;
+  return (int)mm;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout conversion: fp32 NCHW <-> 16-bit NHWC (optionally shifted space-to-depth)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t nhwc_off(int n, int y, int x, int H, int W, int Cp, int b) {
+  if (b == 1) return (((size_t)n * H + y) * W + x) * (size_t)Cp;
+  const int yy = y + (b >> 1), xx = x + (b >> 1);
+  const int by = yy / b, sy = yy - by * b, bx = xx / b, sx = xx - bx * b;
+  const int Hs = H / b + 1, Ws = W / b + 1;
+  return (((((size_t)n * Hs + by) * Ws + bx) * b + sy) * b + sx) * (size_t)Cp;
+}
+
+__global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ in, long long in_bs, uint16_t* __restrict__ out, int C,
+                                        int Cp, int H, int W, int b, int fmt) {
+  const int n = blockIdx.z;
+  const int hw = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    const int y = p / W, x = p - y * W;
+    uint16_t* o = out + nhwc_off(n, y, x, H, W, Cp, b);
+    for (int c = 0; c < Cp; ++c) {
+      const float v = c < C ? in[(size_t)n * in_bs + (size_t)c * hw + p] : 0.f;
+      if (fmt == 0) {
+        __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        o[c] = *reinterpret_cast<uint16_t*>(&h);
+      } else {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        o[c] = *reinterpret_cast<uint16_t*>(&h);
+      }
+    }
+  }
+}
+
+__global__ void nhwc16_to_nchw32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long out_bs, int C,
+                                        int Cp, int H, int W, int b, int fmt) {
+  const int n = blockIdx.z;
+  const int hw = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    const int y = p / W, x = p - y * W;
+    const uint16_t* i = in + nhwc_off(n, y, x, H, W, Cp, b);
+    for (int c = 0; c < C; ++c) {
+      uint16_t u = i[c];
+      float v;
+      if (fmt == 0) v = __half2float(*reinterpret_cast<__half*>(&u));
+      else v = __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+      out[(size_t)n * out_bs + (size_t)c * hw + p] = v;
+    }
+  }
+}
+
+int launch_nchw32_to_nhwc16(const float* in, long long in_bs, const ActDesc& out, int nb, int fmt, cudaStream_t s) {
+  const int hw = out.H * out.W;
+  int bx = std::min(512, (hw + 255) / 256);
+  nchw32_to_nhwc16_kernel<<<dim3(bx, 1, nb), 256, 0, s>>>(in, in_bs, static_cast<uint16_t*>(out.ptr), out.C, out.Cp,
+                                                          out.H, out.W, out.b, fmt);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+int launch_nhwc16_to_nchw32(const ActDesc& in, float* out, long long out_bs, int nb, int fmt, cudaStream_t s) {
+  const int hw = in.H * in.W;
+  int bx = std::min(512, (hw + 255) / 256);
+  nhwc16_to_nchw32_kernel<<<dim3(bx, 1, nb), 256, 0, s>>>(static_cast<const uint16_t*>(in.ptr), out, out_bs, in.C,
+                                                          in.Cp, in.H, in.W, in.b, fmt);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+}  // namespace bp

@@ -1,0 +1,78 @@
+// Window-GEMM convolution engine of the 16-bit path (bp_wconv.cu) -- interface used by bp_v2.cu.
+//
+// Every convolution of the paint path is lowered on the host to one "window GEMM":
+//   D[(R, U)][n] = sum over taps (dl, du), unit elements e:  X[line R*Jy + dl][unit U + du][e] * B[tap][e][n]
+// where X is a 16-bit NHWC activation whose lines are cut into *units* of G stored pixels
+// (unit = G * Cs channels, contiguous in memory), (R, U) enumerates output block-lines / units and
+// column n enumerates (output row jy, output pixel jx, channel) of the Jy x G pixel block the
+// M row produces.  Plain stride-1 convolutions, k = 2s strided convolutions (on the shifted
+// space-to-depth layout their producer writes) and the sub-pixel phases of transposed convolutions
+// all take this form; the Toeplitz expansion of the weights for G > 1 / Jy > 1 happens at pack time.
+#pragma once
+
+#include <functional>
+#include <vector>
+
+#include "bp_common.h"
+
+namespace bp {
+
+// a 16-bit NHWC activation tensor in device memory: [n][Hs][Ws][b*b][Cp]
+//   b == 1: plain (Hs = H, Ws = W)
+//   b  > 1: shifted space-to-depth for a k = 2b, stride b, pad b/2 consumer:
+//           pixel (y, x) lives in block ((y + b/2) / b, (x + b/2) / b), sub-pixel ((y + b/2) % b, (x + b/2) % b);
+//           Hs = H / b + 1; never-written border sub-pixels stay zero (they are the padding)
+// or (f32) a dense fp32 NCHW tensor [n][C][H][W].
+struct ActDesc {
+  void* ptr = nullptr;
+  int C = 0, Cp = 0, H = 0, W = 0, b = 1;
+  bool f32 = false;
+  int Hs() const { return b > 1 ? H / b + 1 : H; }
+  int Ws() const { return b > 1 ? W / b + 1 : W; }
+  size_t elems_per_sample() const { return f32 ? (size_t)C * H * W : (size_t)Hs() * Ws() * b * b * Cp; }
+  size_t bytes_per_sample() const { return elems_per_sample() * (f32 ? 4 : 2); }
+};
+
+struct WTap { int dl, du; };
+struct WSegOff { int oy, ox; };
+
+enum { W_FLAT = 0, W_LINE = 1 };
+
+struct WSpec {
+  // input view: lines of `Wu` units, each unit `unit_elems` 16-bit elements
+  int G = 1, Jy = 1, mode = W_FLAT;
+  int OHl = 0, OWl = 0;                  // M domain: block lines, units per line
+  int nphase = 1;
+  std::vector<WTap> taps[kMaxPhases];
+  std::vector<WSegOff> segs[kMaxPhases];
+  int N = 0;                             // GEMM N (multiple of 16)
+  int seg_len = 0, seg_valid = 0;        // columns per segment / stored channels per segment
+  int ry = 1, rx = 1;                    // output pixel of M row (R, U), segment (oy, ox): (R*ry + oy, U*rx + ox)
+  // weight of (phase, tap, element of the unit, column); BN scale already folded in
+  std::function<float(int, int, int, int)> weight;
+  std::vector<float> shift;              // [N] per column
+  int act = 0;
+  float act_param = 0.f;
+  int fmt = 0;
+};
+
+struct WLayer;   // opaque (bp_wconv.cu)
+
+// builds the packed weights / k-step tables / TMA tensor map for `spec` reading from `in`
+// (whose device pointer must already be final) with capacity for `nb_max` samples
+int wconv_build(const WSpec& spec, const ActDesc& in, int nb_max, WLayer** out);
+void wconv_free(WLayer* w);
+int wconv_launch(const WLayer* w, const ActDesc& out, const void* skip, int nb, cudaStream_t s);
+int wconv_mma_count(const WLayer* w, int nb, double* cycles_floor);
+
+// lowering (bp_v2.cu)
+int v2_padc(int c);
+bool v2_eligible(const Layer& l, int* need_b);
+int v2_make_spec(const Layer& l, int fmt, WSpec* sp);
+int v2_candidates(const Layer& l, int fmt, int Cp, std::vector<WSpec>* out);
+
+// layout conversion kernels
+int launch_nchw32_to_nhwc16(const float* in, long long in_bs, const ActDesc& out, int nb, int fmt, cudaStream_t s);
+int launch_nhwc16_to_nchw32(const ActDesc& in, float* out, long long out_bs, int nb, int fmt, cudaStream_t s);
+
+}  // namespace bp

@@ -33,6 +33,7 @@ struct TArgs {
   uint32_t b_lbo, b_sbo, b_layout, b_kstep;
   int ksteps;                                  // distinct K steps cycled through
   int nacc;                                    // independent TMEM accumulators cycled through
+  uint32_t a_off;                              // extra byte offset of every A start address
   long long* out;
 };
 
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(128, 1) throughput_kernel(TArgs a) {
     uint64_t da[4], db[4];
     uint32_t dt[4];
     for (int i = 0; i < 4; ++i) {
-      da[i] = desc_full(abase + (i % a.ksteps) * a.a_kstep, a.a_lbo, a.a_sbo, a.a_layout, 0);
+      da[i] = desc_full(abase + a.a_off + (i % a.ksteps) * a.a_kstep, a.a_lbo, a.a_sbo, a.a_layout, 0);
       db[i] = desc_full(bbase + (i % a.ksteps) * a.b_kstep, a.b_lbo, a.b_sbo, a.b_layout, 0);
       dt[i] = tm + (a.nacc > 1 ? (uint32_t)((i % a.nacc) * a.n) : 0u);
     }
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(128, 1) semantics_kernel(SArgs a, int swz_bits
     // swizzle: chunk index ^= (row index within the repeating pattern) masked to the swizzle width
     const int rowphase = (p * row_bytes / 128) & 7;     // address bits [7:9] of the row start
     const int cs = c ^ (rowphase & (chunks - 1));
-    P[(size_t)p * (row_bytes / 2) + cs * 8 + e] = __float2half((float)(p * 4 + (c * 8 + e) % 4) + (float)((c * 8 + e) / 4) * 1024.f);
+    P[(size_t)p * (row_bytes / 2) + cs * 8 + e] = __float2half((float)((p * 64 + c * 8 + e) % 2003));
   }
   __half* B = reinterpret_cast<__half*>(smem + 64 * 1024);   // no-swizzle [chunk 0..1][n 0..15][8]
   for (int i = tid; i < 2 * 16 * 8; i += 128) {
@@ -149,7 +150,7 @@ int main() {
   printf("== cycles per tcgen05.mma (M=128, K=16, f16), %d back-to-back, 1 CTA and 148 CTAs ==\n", reps);
   struct L { const char* name; uint32_t lbo_a, sbo, layout, kstep_a; int ksteps; bool lbo_is_n; };
   // lbo for "none/SBO128": A: 128 rows*16 = 2048 ; B: N*16.  K step (2 chunks) advances 2*LBO.
-  for (int layout = 0; layout < 5; ++layout) {
+  for (int layout = 0; layout < 5; layout += 4) {
     for (int n : {16, 32, 64, 128, 256}) {
       TArgs a;
       memset(&a, 0, sizeof(a));
@@ -199,6 +200,47 @@ int main() {
     }
   }
 
+
+  printf("== A start-address alignment / LBO (N=128 and N=32, acc=2, 148 CTAs) ==\n");
+  {
+    struct C { const char* name; uint32_t layout, lbo, sbo, kstep, off; int ksteps; };
+    const C cs[] = {
+      {"none dense  off=0    LBO=2048", 0, 2048, 128, 4096, 0, 4},
+      {"none dense  off=16   LBO=2048", 0, 2048, 128, 4096, 16, 4},
+      {"none dense  off=48   LBO=2048", 0, 2048, 128, 4096, 48, 4},
+      {"none dense  off=64   LBO=2048", 0, 2048, 128, 4096, 64, 4},
+      {"none dense  off=0    LBO=9568", 0, 9568, 128, 19136, 0, 2},
+      {"none dense  off=1072 LBO=9568", 0, 9568, 128, 19136, 1072, 2},
+      {"none dense  off=0    LBO=16 (tap pair)", 0, 16, 128, 32, 0, 4},
+      {"none dense  off=16   LBO=1056 (tap pair)", 0, 1056, 128, 32, 16, 4},
+      {"SW128 off=0", 2, 16, 1024, 32, 0, 4},
+      {"SW128 off=128 (1 row)", 2, 16, 1024, 32, 128, 4},
+      {"SW128 off=384 (3 rows)", 2, 16, 1024, 32, 384, 4},
+      {"SW128 off=8448+640 (66+5 rows)", 2, 16, 1024, 32, 9088, 4},
+      {"SW64  off=0", 4, 16, 512, 32, 0, 2},
+      {"SW64  off=192 (3 rows)", 4, 16, 512, 32, 192, 2},
+      {"SW32  off=0", 6, 16, 256, 4096, 0, 4},
+      {"SW32  off=96 (3 rows)", 6, 16, 256, 4096, 96, 4},
+    };
+    for (const C& c : cs) {
+      for (int n : {32, 128}) {
+        TArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = n; a.reps = reps; a.out = d_out; a.nacc = 2;
+        a.a_lbo = c.lbo; a.a_sbo = c.sbo; a.a_layout = c.layout; a.a_kstep = c.kstep; a.a_off = c.off; a.ksteps = c.ksteps;
+        a.b_lbo = n * 16; a.b_sbo = 128; a.b_layout = 0; a.b_kstep = 2 * n * 16;
+        long long h[2 * 148];
+        throughput_kernel<<<148, 128, 128 * 1024>>>(a);
+        CK(cudaDeviceSynchronize());
+        throughput_kernel<<<148, 128, 128 * 1024>>>(a);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, d_out, 2 * 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+        long long mx = 0;
+        for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("%-44s N=%3d  %7.1f cyc/mma\n", c.name, n, (double)mx / reps);
+      }
+    }
+  }
   printf("== shifted start address on a swizzled K-major A operand ==\n");
   float* d_res;
   CK(cudaMalloc(&d_res, 128 * 16 * sizeof(float)));
@@ -225,7 +267,7 @@ int main() {
           for (int m = 0; m < 128; ++m)
             for (int n = 0; n < 16; ++n) {
               const int chn = kadv * 16 + n;
-              const float exp_v = (float)((m + shift) * 4 + chn % 4) + (float)(chn / 4) * 1024.f;
+              const float exp_v = (float)(((m + shift) * 64 + chn) % 2003);
               const float got = hres[m * 16 + n];
               if (fabsf(got - exp_v) > 0.02f) {
                 if (!bad) { first_got = got; first_exp = exp_v; first_m = m; first_n = n; }
