@@ -403,7 +403,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       ActDesc o; o.C = d.cout; o.H = r.l->OHF; o.W = r.l->OWF;
       const bool next_w = !last && seq[i + 1].w;
       if (d.cout == 1) { o.f32 = true; o.Cp = 1; }
-      else { o.Cp = v2_padc(d.cout); o.b = next_w ? seq[i + 1].need_b : 1; }
+      else { o.Cp = std::max(8, v2_padc(d.cout)); o.b = next_w ? seq[i + 1].need_b : 1; }   // 16-byte stores
       std::vector<WSpec> cands;
       int rc = v2_candidates(*r.l, fmt, Cp, &cands);
       if (rc != BP_OK) return rc;
@@ -450,6 +450,16 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       }
       ops.push_back(op);
     }
+  }
+  if (!caller_out && !P.acts[cur].f32) {
+    // the sequence's consumer (latent sampling) reads fp32 NCHW
+    const ActDesc& c = P.acts[cur];
+    ActDesc a; a.C = c.C; a.Cp = c.C; a.H = c.H; a.W = c.W; a.f32 = true;
+    V2Op cv; cv.kind = V2_TO_F32; cv.in = cur;
+    int rc = v2_new_act(net, a, &cv.out);
+    if (rc != BP_OK) return rc;
+    ops.push_back(cv);
+    cur = cv.out;
   }
   if (last_act) *last_act = cur;
   return BP_OK;

@@ -123,6 +123,20 @@ __device__ __forceinline__ void umma_f16_pred(uint32_t tmem_d, uint64_t desc_a, 
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue));
 }
+
+// same, descriptors given as (low word, high word): only the low word (start address field) changes between
+// MMAs, so the issuing warp's address arithmetic is 32-bit and stays on the uniform datapath
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue));
+}
 __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t issue) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

@@ -29,7 +29,7 @@ bool v2_eligible(const Layer& l, int* need_b) {
   *need_b = 1;
   if (getenv("BP_V2_OFF")) return false;
   if (d.cout > 128 || (d.cout & (d.cout - 1)) != 0) return false;
-  if (d.cout < 8 && !(d.cout == 1 && d.kind == BP_CONV && d.stride == 1)) return false;
+  if (d.cout < 8 && !(d.kind == BP_CONV && d.stride == 1 && (d.cout == 1 || d.cout == 2 || d.cout == 4))) return false;
   if (d.kind == BP_CONV) {
     if (d.stride == 1) return d.kernel == 2 * d.pad + 1;   // unit / packing chosen by v2_candidates
     if (d.kernel != 2 * d.stride || d.pad * 2 != d.stride) return false;

@@ -41,7 +41,7 @@ constexpr int W_SMEM_LIMIT = 227 * 1024;
 constexpr int W_TABLE_SMEM = 256 * 4 + 256;   // shift table + barriers; + patch stages + weight ring
 
 struct WPhase {
-  int nks, stage_begin, seg_begin;     // k-steps (padded to a multiple of ksb), first weight stage, first segment
+  int stage_begin, seg_begin, nseg;    // first weight stage, first segment, segments (columns beyond are padding)
   int dl0, du0, ntl, ntu;              // rectangular tap grid: lines dl0 .. dl0+ntl-1, units du0 .. du0+ntu-1
 };
 
@@ -53,8 +53,9 @@ struct WArgs {
   int ub16;                    // unit block bytes / 16
   int nkb, kbps, nblk;
   uint32_t kb_bytes, stage_bytes, box_bytes, bstage_bytes;
-  int ksb, nbst;               // k-steps per weight stage; weight stages
+  int ksb, nbst;               // k-step slots per weight stage (= glines * run); weight stages
   int kpu;                     // k-steps per unit block (UB / 32)
+  int glines, run, spb;        // tap lines per weight stage, k-steps per tap line (ntu * kpu), stages per patch block
   int nphase, total_segs;
   WPhase phase[kMaxPhases];
   int N, seg_shift, seg_valid;
@@ -150,10 +151,13 @@ __device__ __forceinline__ WRegion w_decode(const WArgs& a, int reg) {
 // Every lane runs the (warp-uniform) descriptor arithmetic so it stays in uniform registers; one elected
 // lane issues.  Descriptors computed inside `if (lane == 0)` live in vector registers and cost a
 // vector->uniform waterfall per UTCHMMA (130-170 cycles per MMA instead of 64; tools/issue_probe.cu).
-// This warp's instruction stream is the kernel's critical path: T_R is compile-time so the per-slice body
-// is straight-line descriptor increments + MMAs, ring indices are compare-and-reset counters (a runtime
-// modulo would drag the descriptors through the vector ALU), and each ~130-cycle full/empty handshake is
-// amortised over ksb*T_R MMAs.
+// This warp's instruction stream is the kernel's critical path (ncu: branch_resolving and the per-k-step
+// bookkeeping dominated earlier versions), so:
+//   * a weight stage is exactly `glines` tap lines: the full/empty handshake (~130 cycles) sits outside the
+//     inner loop and is amortised over glines*run*T_R MMAs; there are no padding MMAs
+//   * the inner loop walks the `run` adjacent 32-byte slices of one tap line: two 32-bit adds + T_R MMAs
+//   * descriptors are carried as 32-bit low words (the high word is constant), T_R is compile-time
+//   * ring indices are compare-and-reset counters (a runtime modulo goes through the vector ALU)
 template <int T_R>
 __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB, uint64_t* bars, uint32_t tmem_base,
                                         long long* tacc) {
@@ -168,82 +172,47 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
   const uint32_t idesc = make_idesc_f16(a.fmt, N);
   const uint64_t db_tmpl = make_smem_desc(0, (uint32_t)N * 16u, 128u);
   const uint64_t da_tmpl = make_smem_desc_sw(0, (uint32_t)a.ub16 * 16u);
-  const uint32_t sB16 = smem_u32(sB) >> 4, sP16 = smem_u32(sP) >> 4;
-  const uint32_t pstage16 = a.stage_bytes >> 4, bstage16 = a.bstage_bytes >> 4, kb16 = a.kb_bytes >> 4;
+  const uint32_t a_hi = (uint32_t)(da_tmpl >> 32), b_hi = (uint32_t)(db_tmpl >> 32);
+  const uint32_t a_lo0 = (uint32_t)da_tmpl + (smem_u32(sP) >> 4), b_lo0 = (uint32_t)db_tmpl + (smem_u32(sB) >> 4);
+  const uint32_t pstage16 = a.stage_bytes >> 4, bstage16 = a.bstage_bytes >> 4;
   const uint32_t bstep16 = 2u * (uint32_t)N;
   const uint32_t ub16 = (uint32_t)a.ub16;
   const uint32_t tile_step16 = (uint32_t)(a.mode == W_LINE ? a.Jy * a.PW : 128) * ub16;
   const uint32_t line_step = (uint32_t)a.PW * ub16;
-  const int ksb = a.ksb, nbst = a.nbst, nblk = a.nblk, kbps = a.kbps, kpu = a.kpu;
+  const int nbst = a.nbst, nblk = a.nblk, glines = a.glines, run = a.run;
   const int total_regions = a.total_regions;
   uint32_t pst = 0, ppar = 0, bst = 0, bpar = 0, as = 0, apar = 0;
-  int kc = 0;
-  uint64_t db = 0;
-
-// one k-step: T_R MMAs sharing the weight slice `db`; handshakes at weight-stage boundaries
-#define W_KSTEP(DA, ACC)                                                                          \
-  do {                                                                                            \
-    if (kc == 0) {                                                                                \
-      W_TWAIT(2, mbar_wait(&full_b[bst], bpar));                                                  \
-      tc_fence_after();                                                                           \
-      db = db_tmpl + (uint64_t)(sB16 + bst * bstage16);                                           \
-    }                                                                                             \
-    _Pragma("unroll") for (int mt = 0; mt < T_R; ++mt)                                            \
-      umma_f16_pred(d_tmem + (uint32_t)(mt * N), (DA) + (uint64_t)((uint32_t)mt * tile_step16), db, idesc, (ACC), el); \
-    db += bstep16;                                                                                \
-    if (++kc == ksb) {                                                                            \
-      umma_commit_pred(&empty_b[bst], el);                                                        \
-      kc = 0;                                                                                     \
-      if (++bst == (uint32_t)nbst) { bst = 0; bpar ^= 1u; }                                       \
-    }                                                                                             \
-  } while (0)
-
   for (int reg = blockIdx.x; reg < total_regions; reg += gridDim.x) {
     const WRegion R = w_decode(a, reg);
     const WPhase P = a.phase[R.pi];
     W_TWAIT(0, mbar_wait(&tempty[as], apar ^ 1u));
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + as * (uint32_t)(T_R * N);
-    const uint32_t row0 = (uint32_t)((a.top + P.dl0) * a.PW + (a.left + P.du0)) * ub16;
-    int ks = 0;
+    const uint32_t row0 = ((uint32_t)((a.top + P.dl0) * a.PW + (a.left + P.du0)) + (uint32_t)R.tile0) * ub16;
     uint32_t acc = 0;
     for (int blk = 0; blk < nblk; ++blk) {
       W_TWAIT(1, mbar_wait(&full_p[pst], ppar));
       tc_fence_after();
-      const uint64_t a_base = da_tmpl + (uint64_t)(sP16 + pst * pstage16 + (uint32_t)R.tile0 * ub16);
-      // k-step order = packing order of the weights: tap line, tap unit, K block of the stage, 32-byte slice
-      if (kbps == 1) {
-        // the units of one tap line are adjacent in the patch: one run of ntu*kpu consecutive 32-byte slices
-        const int run = P.ntu * kpu;
-        uint64_t da_line = a_base + (uint64_t)row0;
-        for (int ti = 0; ti < P.ntl; ++ti, da_line += line_step) {
-          uint64_t da = da_line;
-          for (int sl = 0; sl < run; ++sl, da += 2) {
-            W_KSTEP(da, acc);
+      uint32_t da_line = a_lo0 + pst * pstage16 + row0;
+      for (int l0 = 0; l0 < P.ntl; l0 += glines) {
+        W_TWAIT(2, mbar_wait(&full_b[bst], bpar));
+        tc_fence_after();
+        uint32_t db = b_lo0 + bst * bstage16;
+        const int lend = min(glines, P.ntl - l0);
+        for (int li = 0; li < lend; ++li, da_line += line_step) {
+          uint32_t da = da_line;
+#pragma unroll 2
+          for (int sl = 0; sl < run; ++sl) {
+#pragma unroll
+            for (int mt = 0; mt < T_R; ++mt)
+              umma_f16_lohi(d_tmem + (uint32_t)(mt * N), da + (uint32_t)mt * tile_step16, a_hi, db, b_hi, idesc, acc, el);
             acc = 1u;
+            da += 2u;
+            db += bstep16;
           }
         }
-        ks += P.ntl * run;
-      } else {
-        uint32_t o_line = row0;
-        for (int ti = 0; ti < P.ntl; ++ti, o_line += line_step) {
-          uint32_t o_unit = o_line;
-          for (int tj = 0; tj < P.ntu; ++tj, o_unit += ub16) {
-            uint32_t o = o_unit;
-            for (int j = 0; j < kbps; ++j, o += kb16) {
-              uint64_t da = a_base + (uint64_t)o;
-              for (int k4 = 0; k4 < kpu; ++k4, da += 2) {
-                W_KSTEP(da, acc);
-                acc = 1u;
-              }
-            }
-          }
-        }
-        ks += P.ntl * P.ntu * kbps * kpu;
-      }
-      if (blk == nblk - 1) {
-        // zero-weight padding up to a whole weight stage (any valid A address)
-        for (; ks < P.nks; ++ks) W_KSTEP(a_base, 1u);
+        umma_commit_pred(&empty_b[bst], el);
+        if (++bst == (uint32_t)nbst) { bst = 0; bpar ^= 1u; }
       }
       umma_commit_pred(&empty_p[pst], el);
       if (++pst == 2u) { pst = 0; ppar ^= 1u; }
@@ -251,7 +220,6 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
     umma_commit_pred(&tfull[as], el);
     if (++as == 2u) { as = 0; apar ^= 1u; }
   }
-#undef W_KSTEP
 }
 
 template <int ACT, bool SKIP, bool OUTF32>
@@ -325,7 +293,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
       for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x) {
         const WRegion R = w_decode(a, reg);
         const WPhase P = a.phase[R.pi];
-        const int nst = P.nks / a.ksb;
+        const int nst = a.nblk * a.spb;
         for (int sg = 0; sg < nst; ++sg) {
           W_TWAIT(0, mbar_wait(&empty_b[st], par ^ 1u));
           if (a.dbg & 4) {
@@ -428,7 +396,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
             for (int h = 0; h < 4; ++h) {
               const int n0 = c0 + h * 4;
               const int seg = P.seg_begin + (n0 >> a.seg_shift), ch = n0 & seg_mask;
-              if (ch >= a.seg_valid) continue;                          // warp-uniform
+              if (ch >= a.seg_valid || (n0 >> a.seg_shift) >= P.nseg) continue;   // warp-uniform
               if (!valid || (a.dbg & 2)) continue;
               if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
               float* o = reinterpret_cast<float*>(a.out) + (rbase + a.seg_delta[seg] + ch);
@@ -451,7 +419,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
             for (int h = 0; h < 2; ++h) {
               const int n0 = c0 + h * 8;
               const int seg = P.seg_begin + (n0 >> a.seg_shift), ch = n0 & seg_mask;
-              if (ch >= a.seg_valid) continue;                          // warp-uniform
+              if (ch >= a.seg_valid || (n0 >> a.seg_shift) >= P.nseg) continue;   // warp-uniform
               if (!valid || (a.dbg & 2)) continue;
               if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
               const float4 sa = sh4[h * 2], sb = sh4[h * 2 + 1];
@@ -606,12 +574,22 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
   const int bottom = dl_max - (sp.Jy - 1) > 0 ? dl_max - (sp.Jy - 1) : 0;   // lines below the block's last own line
   const int right = du_max;
 
-  // ---- tiling search: strip width, M-tiles per region, K blocks per patch stage, weight-stage depth.
+  // ---- tiling search: strip width, M-tiles per region, tap lines per weight stage, weight-ring depth.
   // Score = tensor-pipe cycles per useful M row: MMA floor + the ~130-cycle stage handshake amortised over
   // the stage's MMAs, inflated by the discarded halo columns of the flat domain and by weight rings too
-  // shallow to cover the L2 latency.
-  struct Choice { double score; int Wt, T_r, kbps, ksb, nbst; };
-  Choice best{1e30, 0, 0, 0, 0, 0};
+  // shallow to cover the L2 latency.  One K block (128 B of every unit) per patch stage.
+  const int ntu0 = grids[0].ntu;
+  for (const Grid& g : grids)
+    if (g.ntu != ntu0) {
+      delete wl;
+      set_error("window GEMM: phases with different tap-grid widths");
+      return BP_E_UNSUPPORTED;
+    }
+  const int run = ntu0 * kpu;
+  int ntl_max = 0;
+  for (const Grid& g : grids) ntl_max = std::max(ntl_max, g.ntl);
+  struct Choice { double score; int Wt, T_r, gl, nbst; };
+  Choice best{1e30, 0, 0, 0, 0};
   std::vector<int> wts;
   if (sp.mode == W_LINE) {
     wts.push_back(std::min(sp.OWl, 128));
@@ -628,29 +606,27 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
       if (lines > 256) continue;
       const size_t box = (size_t)UB * PW * lines;
       const size_t kb_bytes = (box + (size_t)UB * (a.left + right + 8) + 1023) / 1024 * 1024;
-      for (int kbps = nkb; kbps >= 1; kbps /= 2) {
-        if (nkb % kbps) continue;
-        for (int ksb : {16, 12, 8, 6, 4}) {
-          const size_t bstage = (size_t)sp.N * 32 * ksb;
-          if (bstage > 49152) continue;
-          for (int nbst : {4, 3, 2}) {
-            const size_t smem = W_PSTAGES * kb_bytes * kbps + nbst * bstage + W_TABLE_SMEM;
-            if (smem > (size_t)W_SMEM_LIMIT) continue;
-            const double fl = w_mma_floor(sp.N);
-            double cyc = fl + 130.0 / (ksb * T_r);
-            // padding of the k-step count to whole stages
-            double pad = 0;
-            for (const Grid& g : grids) {
-              const int real = g.ntl * g.ntu * nkb * kpu;
-              pad += (double)((real + ksb - 1) / ksb * ksb) / real;
-            }
-            cyc *= pad / grids.size();
-            if (sp.mode == W_FLAT) cyc *= (double)PW / Wt;
-            const double buffered = (double)nbst * ksb * T_r * fl;
-            if (buffered < 2500.0) cyc *= 1.0 + 0.15 * (2500.0 - buffered) / 2500.0;
-            cyc += 400.0 / (T_r * max_taps * nkb * kpu);          // per-region handshakes
-            if (cyc < best.score) best = Choice{cyc, Wt, T_r, kbps, ksb, nbst};
-          }
+      for (int gl = 1; gl <= ntl_max; ++gl) {
+        const size_t bstage = (size_t)sp.N * 32 * gl * run;
+        if (bstage > 49152) break;
+        for (int nbst : {4, 3, 2}) {
+          const size_t smem = W_PSTAGES * kb_bytes + nbst * bstage + W_TABLE_SMEM;
+          if (smem > (size_t)W_SMEM_LIMIT) continue;
+          const double fl = w_mma_floor(sp.N);
+          // average MMAs per stage over the phases (the last stage of a block may hold fewer lines)
+          double mma_stage = 0;
+          for (const Grid& g : grids) mma_stage += (double)g.ntl * run * T_r / ((g.ntl + gl - 1) / gl);
+          mma_stage /= grids.size();
+          double cyc = fl + 130.0 / mma_stage;
+          // L2 -> SM traffic per MMA: the weight slice is re-streamed for every region (shared by its T_r
+          // M-tiles) and the patch once per region; ~36 B/cycle/SM is sustainable with all SMs loading
+          const double l2_bytes = (double)sp.N * 32.0 / T_r + (double)kb_bytes / (max_taps * kpu * T_r);
+          cyc = std::max(cyc, l2_bytes / 36.0);
+          if (sp.mode == W_FLAT) cyc *= (double)PW / Wt;
+          const double buffered = (double)nbst * mma_stage * fl;
+          if (buffered < 2500.0) cyc *= 1.0 + 0.15 * (2500.0 - buffered) / 2500.0;
+          cyc += 400.0 / (T_r * max_taps * nkb * kpu);          // per-region handshakes
+          if (cyc < best.score) best = Choice{cyc, Wt, T_r, gl, nbst};
         }
       }
     }
@@ -660,7 +636,8 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
     set_error("window GEMM: no tiling of a %d-byte x %d-block unit window fits in shared memory", UB, nkb);
     return BP_E_UNSUPPORTED;
   }
-  a.Wt = best.Wt; a.T_r = best.T_r; a.kbps = best.kbps; a.ksb = best.ksb; a.nbst = best.nbst;
+  a.Wt = best.Wt; a.T_r = best.T_r; a.kbps = 1; a.nbst = best.nbst;
+  a.glines = best.gl; a.run = run; a.ksb = best.gl * run;
   a.PW = a.Wt + a.left + right;
   a.nstrips = (sp.OWl + a.Wt - 1) / a.Wt;
   if (sp.mode == W_LINE) a.lines = a.T_r * sp.Jy + a.top + bottom;
@@ -668,9 +645,9 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
   a.box_bytes = (uint32_t)UB * a.PW * a.lines;
   // slack: garbage M rows of the last tile read up to (left + right) units past the box
   a.kb_bytes = (uint32_t)(((size_t)a.box_bytes + (size_t)UB * (a.left + right + 8) + 1023) / 1024 * 1024);
-  a.stage_bytes = a.kb_bytes * a.kbps;
+  a.stage_bytes = a.kb_bytes;
   a.bstage_bytes = (uint32_t)sp.N * 32u * (uint32_t)a.ksb;
-  a.nblk = nkb / a.kbps;
+  a.nblk = nkb;
   if (sp.mode == W_LINE) a.regs_per_strip = (sp.OHl + a.T_r - 1) / a.T_r;
   else a.regs_per_strip = (sp.OHl * a.PW + a.T_r * 128 - 1) / (a.T_r * 128);
   uint32_t cols = 32;
@@ -678,10 +655,13 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
   BP_REQUIRE(cols <= 512, BP_E_UNSUPPORTED, "window GEMM: accumulators exceed TMEM");
   a.tmem_cols = cols;
 
-  // ---- packed weights (k-step order = the MMA issuer's loop nest: block, tap line, tap unit, K block, slice)
+  // ---- packed weights: [phase][K block][stage of glines tap lines][k-step slot][chunk half][N][8]; the
+  // slots of a stage follow the issuer's walk (tap line, tap unit, 32-byte slice); a partial last stage
+  // leaves its tail slots zero (they are never read)
   std::vector<uint16_t> wp;
   std::vector<int2> segs;
   int stage_total = 0;
+  a.spb = 0;
   for (int pi = 0; pi < sp.nphase; ++pi) {
     WPhase& P = a.phase[pi];
     const Grid& g = grids[pi];
@@ -689,27 +669,31 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
     P.stage_begin = stage_total;
     P.seg_begin = (int)segs.size();
     for (const WSegOff& sg : sp.segs[pi]) segs.push_back(make_int2(sg.oy, sg.ox));
-    const int ntaps = g.ntl * g.ntu;
-    const int real = ntaps * nkb * kpu;
-    P.nks = (real + a.ksb - 1) / a.ksb * a.ksb;
-    wp.resize((size_t)(stage_total + P.nks / a.ksb) * a.ksb * 2 * a.N * 8, 0);
-    int ks = 0;
-    for (int blk = 0; blk < a.nblk; ++blk)
-      for (int t = 0; t < ntaps; ++t)
-        for (int j = 0; j < a.kbps; ++j)
-          for (int k4 = 0; k4 < kpu; ++k4, ++ks) {
-            const int kb = blk * a.kbps + j;
-            const int stage = stage_total + ks / a.ksb, kin = ks % a.ksb;
+    P.nseg = (int)sp.segs[pi].size();
+    const int spb = (g.ntl + a.glines - 1) / a.glines;
+    if (pi == 0) a.spb = spb;
+    if (spb != a.spb) {
+      delete wl;
+      set_error("window GEMM: phases with different tap-line counts");
+      return BP_E_UNSUPPORTED;
+    }
+    wp.resize((size_t)(stage_total + nkb * spb) * a.ksb * 2 * a.N * 8, 0);
+    for (int kb = 0; kb < nkb; ++kb)
+      for (int ti = 0; ti < g.ntl; ++ti)
+        for (int tj = 0; tj < g.ntu; ++tj)
+          for (int k4 = 0; k4 < kpu; ++k4) {
+            const int stage = stage_total + kb * spb + ti / a.glines;
+            const int slot = (ti % a.glines) * run + tj * kpu + k4;
             for (int half = 0; half < 2; ++half)
               for (int n = 0; n < a.N; ++n)
                 for (int e = 0; e < 8; ++e) {
                   const int elem = kb * (UB / 2) + k4 * 16 + half * 8 + e;
-                  const float w = sp.weight(pi, g.index[t], elem, n);
-                  if (w != 0.f) wp[((((size_t)stage * a.ksb + kin) * 2 + half) * a.N + n) * 8 + e] = w_to16(w, sp.fmt);
+                  const float w = sp.weight(pi, g.index[(size_t)ti * g.ntu + tj], elem, n);
+                  if (w != 0.f) wp[((((size_t)stage * a.ksb + slot) * 2 + half) * a.N + n) * 8 + e] = w_to16(w, sp.fmt);
                 }
           }
-    stage_total += P.nks / a.ksb;
-    wl->mmas_per_region[pi] = (long long)P.nks * a.T_r;
+    stage_total += nkb * spb;
+    wl->mmas_per_region[pi] = (long long)g.ntl * run * nkb * a.T_r;
   }
   a.total_segs = (int)segs.size();
   if (a.total_segs > W_MAX_SEGS) {
@@ -839,9 +823,9 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
     double floor_cyc = 0;
     const long long mm = wconv_mma_count(wl, nb, &floor_cyc);
     fprintf(stderr,
-            "[wconv] N=%d T_r=%d ksb=%d nbst=%d mode=%d ub=%d nkb=%d/%d PW=%d lines=%d regions/cta=%.1f mma/cta=%.0f floor=%.0f total=%.0f cyc"
+            "[wconv] N=%d T_r=%d ksb=%dx%d nbst=%d mode=%d ub=%d nkb=%d PW=%d lines=%d regions/cta=%.1f mma/cta=%.0f floor=%.0f total=%.0f cyc"
             " | waits: A-prod %.0f B-prod %.0f mma:tempty %.0f mma:full_p %.0f mma:full_b %.0f epi:tfull %.0f\n",
-            a.N, a.T_r, a.ksb, a.nbst, a.mode, a.ub16 * 16, a.nkb, a.kbps, a.PW, a.lines, (double)a.total_regions / grid, (double)mm / grid,
+            a.N, a.T_r, a.glines, a.run, a.nbst, a.mode, a.ub16 * 16, a.nkb, a.PW, a.lines, (double)a.total_regions / grid, (double)mm / grid,
             floor_cyc / grid, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
   }
   return BP_OK;
