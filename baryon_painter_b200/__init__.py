@@ -6,3 +6,9 @@ Drop-in surface (same names as the reference package):
 """
 
 __version__ = "0.1.0"
+
+
+def pinned_empty(shape, dtype="float32"):
+    """Page-locked numpy array for zero-staging host transfers (see ``_lib.pinned_empty``)."""
+    from ._lib import pinned_empty as _pe
+    return _pe(shape, dtype)

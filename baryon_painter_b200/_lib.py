@@ -29,7 +29,7 @@ EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destro
            "bp_cvae_paint_host", "bp_cvae_read_prior", "bp_cgan_paint", "bp_cgan_paint_host",
            "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize",
            "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
-           "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile",
+           "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile", "bp_net_chunk",
            "bp_last_error", "bp_version")
 
 
@@ -76,6 +76,8 @@ def load():
     lib.bp_launch_count.argtypes = [i32]
     lib.bp_net_flops_per_tile.restype = ctypes.c_double
     lib.bp_net_flops_per_tile.argtypes = [vp]
+    lib.bp_net_chunk.restype = ctypes.c_int
+    lib.bp_net_chunk.argtypes = [vp]
     lib.bp_cvae_create.argtypes = [ctypes.POINTER(CvaeDesc), i32, i32, i32, ctypes.POINTER(vp)]
     lib.bp_cgan_create.argtypes = [ctypes.POINTER(LayerDesc), i32, i32, i32, i32, i32, i32, ctypes.POINTER(vp)]
     lib.bp_net_destroy.argtypes = [vp]
@@ -181,6 +183,10 @@ class Net:
     def flops_per_tile(self):
         return load().bp_net_flops_per_tile(self.handle)
 
+    @property
+    def chunk(self):
+        return int(load().bp_net_chunk(self.handle))
+
     # -- helpers -------------------------------------------------------------------------
     @staticmethod
     def _tp(sigma_in, sigma_out, aux, k_in, shift_in, k_out, shift_out):
@@ -189,12 +195,16 @@ class Net:
         tp = TransformParams(_fptr(sigma_in), _fptr(sigma_out), _fptr(aux), k_in, shift_in, k_out, shift_out)
         return tp, (sigma_in, sigma_out, aux)
 
-    def cvae_paint_host(self, tiles, latent, mode, seed, tparams, flags):
-        """tiles float32 [n,H,W] (host) -> float32 [n,H,W]."""
+    def cvae_paint_host(self, tiles, latent, mode, seed, tparams, flags, out=None):
+        """tiles float32 [n,H,W] (host) -> float32 [n,H,W].  ``out``: optional C-contiguous float32 result
+        buffer (e.g. page-locked, see ``pinned_empty``), else a fresh array."""
         lib = load()
         n = tiles.shape[0]
         tiles = np.ascontiguousarray(tiles, np.float32)
-        out = np.empty((n, *self.tile_hw), np.float32)
+        if out is None:
+            out = np.empty((n, *self.tile_hw), np.float32)
+        elif out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (n, *self.tile_hw):
+            raise ValueError("out must be a C-contiguous float32 array of shape %r" % ((n, *self.tile_hw),))
         lat = None if latent is None else np.ascontiguousarray(latent, np.float32)
         tp, keep = self._tp(*tparams)
         check(lib.bp_cvae_paint_host(self.handle, tiles.ctypes.data, lat.ctypes.data if lat is not None else None,
@@ -264,3 +274,27 @@ class Net:
 
 def launch_count(reset=False):
     return int(load().bp_launch_count(int(bool(reset))))
+
+
+def stitch_accumulate(num_ptr, den_ptr, n_pixel_plane, tiles_ptr, origins_ptr, n, tile_size, falloff, sigma, stream=0):
+    """Device pointers: float64 numerator / denominator planes, float32 tiles [n,T,T], int32 origins [n,2]."""
+    check(load().bp_stitch_accumulate(num_ptr, den_ptr, int(n_pixel_plane), tiles_ptr, origins_ptr, int(n),
+                                      int(tile_size), float(falloff), float(sigma), stream))
+
+
+def stitch_finalize(num_ptr, den_ptr, plane_ptr, n_pixels, stream=0):
+    check(load().bp_stitch_finalize(num_ptr, den_ptr, plane_ptr, int(n_pixels), stream))
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """Page-locked numpy array (torch owns the allocation): the host entry points DMA straight from / into
+    such buffers instead of staging through the library's own pinned memory."""
+    import torch
+    t = torch.empty(tuple(int(v) for v in np.atleast_1d(shape)), dtype=getattr(torch, np.dtype(dtype).name),
+                    pin_memory=True)
+    a = t.numpy()
+    _PINNED_KEEPALIVE[a.ctypes.data] = t
+    return a
+
+
+_PINNED_KEEPALIVE = {}

@@ -187,7 +187,8 @@ struct bp_net {
   float *h_in = nullptr, *h_out = nullptr, *h_lat = nullptr;
   float *var_mean = nullptr, *var_m2 = nullptr;
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr, out_stream = nullptr;
+  std::vector<cudaEvent_t> ev_ready, ev_chunk_done, ev_out;   // per chunk of the pipelined host path
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int prior_valid = 0;
   bool debug = false;
@@ -252,6 +253,9 @@ static void destroy_net(bp_net* net) {
   }
   if (net->stream) cudaStreamDestroy(net->stream);
   if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
+  if (net->out_stream) cudaStreamDestroy(net->out_stream);
+  for (auto* v : {&net->ev_ready, &net->ev_chunk_done, &net->ev_out})
+    for (cudaEvent_t e : *v) cudaEventDestroy(e);
   delete net;
 }
 
@@ -302,6 +306,7 @@ static int finish_create(bp_net* net) {
   BP_CUDA_TRY(cudaMallocHost(&net->h_out, sizeof(float) * HW * net->max_batch));
   BP_CUDA_TRY(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
   BP_CUDA_TRY(cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking));
+  BP_CUDA_TRY(cudaStreamCreateWithFlags(&net->out_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_in[i], cudaEventDisableTiming));
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_done[i], cudaEventDisableTiming));
@@ -824,8 +829,16 @@ static int cvae_chunk_back(bp_net* net, const float* tiles, const float* latent,
   return run_stack(net, ST_MU, h, out, (long long)HW, post, nb, s, nullptr);
 }
 
+// per-chunk hooks of the pipelined host path: the compute stream waits for `ready[c]` (inputs of chunk c are on the
+// device) before the chunk's first kernel and records `done[c]` after its last one
+struct ChunkHooks {
+  std::vector<cudaEvent_t>* ready = nullptr;
+  std::vector<cudaEvent_t>* done = nullptr;
+};
+
 static int cvae_paint_device(bp_net* net, const float* tiles, const float* latent, int mode, uint64_t seed,
-                             const bp_transform_params* tp, int flags, float* out, int n, cudaStream_t s) {
+                             const bp_transform_params* tp, int flags, float* out, int n, cudaStream_t s,
+                             const ChunkHooks* hooks = nullptr) {
   BP_REQUIRE(net && net->kind == NET_CVAE, BP_E_INVALID, "not a CVAE network");
   BP_REQUIRE(n >= 0 && n <= net->max_batch, BP_E_INVALID, "batch %d exceeds max_batch %d", n, net->max_batch);
   BP_REQUIRE(mode == BP_LATENT_GIVEN || mode == BP_LATENT_EPS || mode == BP_LATENT_SEED, BP_E_INVALID,
@@ -843,6 +856,7 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
   for (int c0 = 0; c0 < n; c0 += net->chunk) {
     const int nb = std::min(net->chunk, n - c0);
     float* prior_out = nullptr;
+    if (hooks && hooks->ready) BP_CUDA_TRY(cudaStreamWaitEvent(s, (*hooks->ready)[c0 / net->chunk], 0));
     rc = cvae_chunk_front(net, tiles, tp, flags, c0, nb, mode != BP_LATENT_GIVEN, s, &prior_out);
     if (rc != BP_OK) return rc;
     const float* lat;
@@ -857,6 +871,7 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
     }
     rc = cvae_chunk_back(net, tiles, lat, tp, flags, c0, nb, out + (size_t)c0 * HW, s);
     if (rc != BP_OK) return rc;
+    if (hooks && hooks->done) BP_CUDA_TRY(cudaEventRecord((*hooks->done)[c0 / net->chunk], s));
     if (net->debug) break;  // debug buffers hold one chunk
   }
   if (mode != BP_LATENT_GIVEN) net->prior_valid = n;
@@ -1006,6 +1021,20 @@ int bp_cgan_paint(bp_net* net, const float* tiles, const bp_transform_params* tp
   return cgan_paint_device(net, tiles, tp, flags, out, n, (cudaStream_t)stream);
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Host buffers in, host buffers out.  The batch is processed in the network's chunks on three streams:
+// copy-in (H2D of chunk c+1), compute (chunk c), copy-out (D2H of chunk c-1), chained by events, so PCIe traffic in
+// both directions overlaps the kernels.  Buffers that are already page-locked (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory) are used in place; pageable ones are staged through the network's pinned buffers, chunk by chunk,
+// while the device works on the previous chunk.
 int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int latent_mode, uint64_t seed,
                        const bp_transform_params* tp, int flags, float* out, int n) {
   BP_REQUIRE(net && net->kind == NET_CVAE, BP_E_INVALID, "not a CVAE network");
@@ -1015,19 +1044,53 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   BP_REQUIRE(latent_mode == BP_LATENT_SEED || latent != nullptr, BP_E_INVALID, "latent/eps array missing");
   BP_CUDA_TRY(cudaSetDevice(net->device));
   const size_t HW = (size_t)net->H * net->W, lhw = (size_t)net->lh * net->lw;
-  cudaStream_t s = net->stream;
-  // stage through pinned memory so the copies are truly asynchronous DMA transfers
-  memcpy(net->h_in, tiles, sizeof(float) * HW * n);
-  BP_CUDA_TRY(cudaMemcpyAsync(net->d_in, net->h_in, sizeof(float) * HW * n, cudaMemcpyHostToDevice, s));
+  cudaStream_t s = net->stream, sin = net->copy_stream, sout = net->out_stream;
+  const int nchunks = (n + net->chunk - 1) / net->chunk;
+  while ((int)net->ev_ready.size() < nchunks) {
+    cudaEvent_t a, b, c;
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+    net->ev_ready.push_back(a); net->ev_chunk_done.push_back(b); net->ev_out.push_back(c);
+  }
+  const bool in_pinned = is_pinned(tiles), out_pinned = is_pinned(out);
   if (latent_mode != BP_LATENT_SEED) {
     memcpy(net->h_lat, latent, sizeof(float) * lhw * n);
-    BP_CUDA_TRY(cudaMemcpyAsync(net->d_lat, net->h_lat, sizeof(float) * lhw * n, cudaMemcpyHostToDevice, s));
+    BP_CUDA_TRY(cudaMemcpyAsync(net->d_lat, net->h_lat, sizeof(float) * lhw * n, cudaMemcpyHostToDevice, sin));
   }
-  int rc = cvae_paint_device(net, net->d_in, net->d_lat, latent_mode, seed, tp, flags, net->d_out, n, s);
+  // inputs: chunk by chunk on the copy-in stream (staging a pageable chunk overlaps the device's work on earlier ones)
+  for (int c = 0; c < nchunks; ++c) {
+    const size_t c0 = (size_t)c * net->chunk, nb = std::min((size_t)net->chunk, (size_t)n - c0);
+    const float* src = tiles + c0 * HW;
+    if (!in_pinned) {
+      memcpy(net->h_in + c0 * HW, src, sizeof(float) * HW * nb);
+      src = net->h_in + c0 * HW;
+    }
+    BP_CUDA_TRY(cudaMemcpyAsync(net->d_in + c0 * HW, src, sizeof(float) * HW * nb, cudaMemcpyHostToDevice, sin));
+    BP_CUDA_TRY(cudaEventRecord(net->ev_ready[c], sin));
+  }
+  ChunkHooks hooks;
+  hooks.ready = &net->ev_ready; hooks.done = &net->ev_chunk_done;
+  int rc = cvae_paint_device(net, net->d_in, net->d_lat, latent_mode, seed, tp, flags, net->d_out, n, s, &hooks);
   if (rc != BP_OK) return rc;
-  BP_CUDA_TRY(cudaMemcpyAsync(net->h_out, net->d_out, sizeof(float) * HW * n, cudaMemcpyDeviceToHost, s));
+  const int done_chunks = net->debug ? 1 : nchunks;
+  for (int c = 0; c < done_chunks; ++c) {
+    const size_t c0 = (size_t)c * net->chunk, nb = std::min((size_t)net->chunk, (size_t)n - c0);
+    float* dst = out_pinned ? out + c0 * HW : net->h_out + c0 * HW;
+    BP_CUDA_TRY(cudaStreamWaitEvent(sout, net->ev_chunk_done[c], 0));
+    BP_CUDA_TRY(cudaMemcpyAsync(dst, net->d_out + c0 * HW, sizeof(float) * HW * nb, cudaMemcpyDeviceToHost, sout));
+    BP_CUDA_TRY(cudaEventRecord(net->ev_out[c], sout));
+  }
+  if (!out_pinned) {
+    for (int c = 0; c < done_chunks; ++c) {
+      const size_t c0 = (size_t)c * net->chunk, nb = std::min((size_t)net->chunk, (size_t)n - c0);
+      BP_CUDA_TRY(cudaEventSynchronize(net->ev_out[c]));
+      memcpy(out + c0 * HW, net->h_out + c0 * HW, sizeof(float) * HW * nb);
+    }
+  }
+  BP_CUDA_TRY(cudaStreamSynchronize(sout));
   BP_CUDA_TRY(cudaStreamSynchronize(s));
-  memcpy(out, net->h_out, sizeof(float) * HW * n);
+  BP_CUDA_TRY(cudaStreamSynchronize(sin));
   return BP_OK;
 }
 
@@ -1135,6 +1198,7 @@ int bp_net_read_activation(bp_net* net, int stack, int layer, float* out, size_t
 }
 
 double bp_net_flops_per_tile(const bp_net* net) { return net ? net->flops_per_tile : 0.0; }
+int bp_net_chunk(const bp_net* net) { return net ? net->chunk : 0; }
 
 int bp_net_set_profile(bp_net* net, int on) {
   BP_REQUIRE(net, BP_E_INVALID, "null net");

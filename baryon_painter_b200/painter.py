@@ -198,10 +198,12 @@ class CVAEPainter(Painter):
         return s_in, s_out, tp
 
     def paint_batch(self, tiles, z=0.0, latents=None, eps=None, seed=None, transform=True,
-                    inverse_transform=True):
+                    inverse_transform=True, out=None):
         """Paint N tiles.  ``tiles`` (N,H,W); ``z`` scalar or (N,).  ``latents`` (N,1,h,w) are used
         as the latent z directly (prior network skipped); ``eps`` (N,1,h,w) replaces the normal draw of
         ``sample_z``; with neither, eps is drawn on the device from ``seed``.
+        ``out``: optional float32 (N,H,W) result buffer; with page-locked ``tiles`` / ``out``
+        (``baryon_painter_b200.pinned_empty``) the copies are direct DMA transfers overlapped with the kernels.
         Returns float32 (N,H,W) [(N,1,H,W) if ``inverse_transform=False``]."""
         tiles = np.asarray(tiles)
         n = tiles.shape[0]
@@ -223,7 +225,7 @@ class CVAEPainter(Painter):
         y_shape = tiles.shape[1:] if tiles.ndim == 4 else (1, *tiles.shape[1:])
         if tuple(y_shape) != tuple(self.model.dim_y):
             raise ValueError(f"Shape mismatch between input and model: {tiles.shape[1:]} vs {self.model.dim_y}")
-        tiles = np.ascontiguousarray(tiles.reshape(n, *self.model.dim_y[1:]), np.float32)
+        tiles = np.ascontiguousarray(tiles.reshape(n, *self.model.dim_y[1:]), np.float32)   # no copy if already so
         if latents is not None and eps is not None:
             raise ValueError("give either latents or eps, not both")
         lat_shape = (n, *self.model.dim_z[1:])
@@ -237,18 +239,56 @@ class CVAEPainter(Painter):
         s_in, s_out, tp = self._sigmas(zs, fuse_t, fuse_i)
         flags = (_lib.BP_FLAG_TRANSFORM if fuse_t else 0) | (_lib.BP_FLAG_INVERSE if fuse_i else 0)
         aux = zs.astype(np.float32)
-        out = np.empty((n, *self.model.dim_y[1:]), np.float32)
+        if out is None:
+            out = np.empty((n, *self.model.dim_y[1:]), np.float32)
+        elif out.shape != (n, *self.model.dim_y[1:]) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape %r" % ((n, *self.model.dim_y[1:]),))
         mb = self.model.max_batch
         for i0 in range(0, n, mb):
             sl = slice(i0, min(n, i0 + mb))
-            out[sl] = self.model.net.cvae_paint_host(
+            self.model.net.cvae_paint_host(
                 tiles[sl], None if lat is None else lat[sl], mode, seed + i0,
-                (None if s_in is None else s_in[sl], None if s_out is None else s_out[sl], aux[sl], *tp), flags)
+                (None if s_in is None else s_in[sl], None if s_out is None else s_out[sl], aux[sl], *tp), flags,
+                out=out[sl])
         if use_i and not fuse_i:
             return np.stack([self.inverse_transform(o.reshape(1, 1, *o.shape), field=self.label_fields[0],
                                                     z=float(zz)) for o, zz in zip(out, zs)])
         if not use_i:
             return out.reshape(n, 1, *out.shape[1:])
+        return out
+
+    def paint_batch_device(self, tiles, z=0.0, eps=None, latents=None, seed=None, out=None):
+        """Device-resident variant of ``paint_batch`` for callers that keep tiles on the GPU (the lightcone
+        loop): ``tiles`` float32 CUDA tensor (N,H,W) on this painter's device, result in ``out`` (allocated if
+        None).  Transforms are the fused fiducial ones."""
+        import torch
+        n = int(tiles.shape[0])
+        if tuple(tiles.shape[1:]) != tuple(self.model.dim_y[1:]):
+            raise ValueError(f"Shape mismatch between input and model: {tuple(tiles.shape[1:])} vs {self.model.dim_y}")
+        if not (tiles.is_cuda and tiles.dtype == torch.float32 and tiles.is_contiguous()):
+            raise ValueError("tiles must be a contiguous float32 CUDA tensor")
+        if out is None:
+            out = torch.empty_like(tiles)
+        zs = np.broadcast_to(np.asarray(z, np.float64).reshape(-1), (n,))
+        s_in, s_out, tp = self._sigmas(zs, True, True)
+        flags = _lib.BP_FLAG_TRANSFORM | _lib.BP_FLAG_INVERSE
+        aux = zs.astype(np.float32)
+        if latents is not None:
+            mode, lat = _lib.BP_LATENT_GIVEN, latents
+        elif eps is not None:
+            mode, lat = _lib.BP_LATENT_EPS, eps
+        else:
+            mode, lat = _lib.BP_LATENT_SEED, None
+        if lat is not None and not (lat.is_cuda and lat.dtype == torch.float32 and lat.is_contiguous()):
+            raise ValueError("latents / eps must be contiguous float32 CUDA tensors")
+        seed = self._next_seed() if seed is None else int(seed)
+        stream = torch.cuda.current_stream(tiles.device).cuda_stream
+        mb = self.model.max_batch
+        for i0 in range(0, n, mb):
+            i1 = min(n, i0 + mb)
+            self.model.net.cvae_paint_device(tiles[i0:i1].data_ptr(), 0 if lat is None else lat[i0:i1].data_ptr(), mode,
+                                             seed + i0, (s_in[i0:i1], s_out[i0:i1], aux[i0:i1], *tp), flags,
+                                             out[i0:i1].data_ptr(), i1 - i0, stream)
         return out
 
     def paint(self, input, z=0.0, transform=True, inverse_transform=True, latent=None, eps=None, seed=None):

@@ -98,7 +98,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count()
-    sample = max(1, min(args.tiles, 8))
+    sample = max(1, min(args.tiles, 64))
     for _ in range(args.warmup):
         cpu_baseline(1, threads, warmup=0)
     t0 = time.perf_counter()
@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=256)
     ap.add_argument("--precision", default=os.environ.get("BARYON_PAINTER_PRECISION", "fp16"))
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-tiles", type=int, default=6, help="tiles in the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-tiles", type=int, default=256, help="tiles in the bounded cpu_baseline sample (about 10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="print the per-layer timing table to stderr")
     args = ap.parse_args()
@@ -194,15 +194,22 @@ def main():
     if not np.all(np.isfinite(d_out[:2].cpu().numpy())):
         raise RuntimeError("non-finite painted tiles")
 
-    # ---- end to end through the public API, host buffers in and out
+    # ---- end to end through the public API: host buffers in and out (page-locked, as the contract's
+    # "pinned host memory"), every step copies its inputs H2D and its painted tiles D2H inside the timed region
+    import baryon_painter_b200 as bp
+    tiles_p = bp.pinned_empty(tiles_h.shape)
+    tiles_p[...] = tiles_h
+    out_h = bp.pinned_empty(tiles_h.shape)
     for _ in range(2):
-        painter.paint_batch(tiles_h, z=0.0, eps=eps_h)
+        painter.paint_batch(tiles_p, z=0.0, eps=eps_h, out=out_h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_h = painter.paint_batch(tiles_h, z=0.0, eps=eps_h)
+        painter.paint_batch(tiles_p, z=0.0, eps=eps_h, out=out_h)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if not np.all(np.isfinite(out_h[-1])):
+        raise RuntimeError("non-finite painted tiles (host path)")
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -231,9 +238,16 @@ def main():
         dom_launches = sum(r[4] for r in dom) or 1
         ach = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
         whole = total_tiles / world * FLOPS_PER_TILE / (ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "3x3 128->128 @64x64 residual-block convolution (8 layers)",
+        traffic = None
+        try:   # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"] if tj.get("tiles_per_launch") == painter.model.net.chunk else None
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "wconv_kernel: 3x3 128->128 @64x64 residual-block convolution (8 layers)",
                 "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                "traffic": None, "peak_source": pk["source"], "launch_ms": dom_ms / dom_launches,
+                "traffic": traffic, "peak_source": pk["source"], "launch_ms": dom_ms / dom_launches,
                 "share_of_step": dom_ms / tot,
                 "whole_net": {"achieved": whole, "frac": whole / pk["bf16_tflops"],
                               "flops_per_tile": FLOPS_PER_TILE}}

@@ -169,6 +169,8 @@ int bp_net_read_profile(bp_net* net, int stack, int layer, double* total_ms, int
 int bp_net_layer_info(const bp_net* net, int stack, int layer, double* flops, int* geom);
 /* kernels launched by this library on this thread since the last reset */
 int64_t bp_launch_count(int reset);
+/* tiles processed per internal launch group (layer outputs of one chunk are kept L2-/HBM-resident together) */
+int bp_net_chunk(const bp_net* net);
 /* algorithmic FLOPs (2*MACs) per tile of the network's convolutions */
 double bp_net_flops_per_tile(const bp_net* net);
 const char* bp_last_error(void);

@@ -22,6 +22,9 @@ TOL = {"fp32": 1e-4, "fp16": 1e-2, "bf16": 1e-1}
 TOL_XMU = {"fp32": 1e-5, "fp16": 2e-3, "bf16": 1e-2}
 # layer-boundary tensors: fp32 accumulates ~1e-6 per layer; fp16 ~ 4e-4, bf16 ~ 3e-3 per layer
 TOL_LAYER = {"fp32": 2e-5, "fp16": 3e-3, "bf16": 2e-2}
+# (z_mu, z_log_var) of the t64 fixture are 2x2 maps with one or two non-zero entries after the ReLU, so a single
+# element's rounding through the four 16-bit prior layers is the whole norm
+TOL_PRIOR = {"fp32": 2e-5, "fp16": 3e-3, "bf16": 5e-2}
 PRECISIONS = ["fp32", "fp16", "bf16"]
 
 
@@ -78,8 +81,8 @@ def test_layer_boundaries_t64(precision):
             worst = max(worst, e)
             assert e <= TOL_LAYER[precision], (k, li, e)
     mu, lv = p.model.net.cvae_read_prior(1)
-    assert rel_l2(mu[0], g["z_mu"][0][0]) <= TOL_LAYER[precision]
-    assert rel_l2(lv[0], g["z_log_var"][0][0]) <= TOL_LAYER[precision] or np.abs(g["z_log_var"]).max() < 1e-6
+    assert rel_l2(mu[0], g["z_mu"][0][0]) <= TOL_PRIOR[precision]
+    assert rel_l2(lv[0], g["z_log_var"][0][0]) <= TOL_PRIOR[precision] or np.abs(g["z_log_var"]).max() < 1e-6
     print("worst layer rel-L2", precision, worst)
 
 

@@ -1,0 +1,80 @@
+"""Lightcone path on the GPU: device stitching (C ABI bp_stitch_*) against the reference golden, and the full
+tile loop -- batched CUDA painting + device stitching -- against the oracle painter + numpy restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_stitch_matches_reference_golden():
+    from oracle import slics_oracle as so
+    from baryon_painter_b200 import process_SLICS as ps
+    from test_lightcone import _case
+    g, args = _case()
+    planes = ps.process_SLICS(so.StubPainter(), **args)            # default backend: device
+    for i, p in enumerate(planes):
+        assert p.shape == g[f"plane{i}"].shape and p.dtype == np.float64
+        # float64 atomics: summation order differs from the host loop in the last bits only
+        assert np.allclose(p, g[f"plane{i}"], rtol=1e-12, atol=0), i
+
+
+class _FixedEps:
+    """paint with eps = 0 (latent = z_mu) so the device and oracle runs see the same latents"""
+
+    def __init__(self, painter):
+        self.p = painter
+        self.compute_device = painter.compute_device
+
+    def paint_batch_device(self, tiles, z=0.0, out=None):
+        import torch
+        eps = torch.zeros((tiles.shape[0], *self.p.model.dim_z[1:]), dtype=torch.float32, device=tiles.device)
+        return self.p.paint_batch_device(tiles, z=z, eps=eps, out=out)
+
+
+class _OraclePainter:
+    compute_device = None
+
+    def __init__(self, tile, seed):
+        from oracle.cvae_oracle import CVAEOracle
+        from baryon_painter_b200 import arch, synthetic, transforms
+        A = arch.fiducial_cvae_architecture(tile)
+        self.o = CVAEOracle(A, synthetic.synthetic_cvae_state_dict(A, seed=seed))
+        self.stats = transforms.fiducial_stats()
+        self.lat = (tile // 32, tile // 32)
+
+    def paint(self, input, z=0.0, transform=True, inverse_transform=True):
+        return self.o.paint(np.asarray(input, np.float32), float(z), self.stats, eps=np.zeros((1, 1, *self.lat), np.float32))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
+def test_tile_loop_vs_oracle(precision, tol):
+    from oracle import slics_oracle as so
+    from baryon_painter_b200 import process_SLICS as ps
+    from baryon_painter_b200.painter import CVAEPainter
+    tile = 64
+    rng = np.random.default_rng(5)
+    import scipy.ndimage
+
+    def field(n):     # smooth positive density (a cubic zoom of white noise overshoots below zero -> log of negatives)
+        g = scipy.ndimage.gaussian_filter(rng.standard_normal((n, n)), 4.0, mode="wrap")
+        return np.exp(g / g.std() - 0.5).astype(np.float32)
+
+    planes_in = {1: field(400), 2: field(500)}
+    args = dict(tile_size=100.0, n_pixel_tile=tile, LOS=1, z_SLICS=[0.2, 0.5], delta_size=[150.0, 230.0],
+                delta_path=None, massplane_path=None, shifts_path=np.zeros((2, 2)), z_slice=[0.21, 0.52], verbose=False,
+                plane_source=lambda i, kind: planes_in[i + 1])
+    dev = ps.process_SLICS(_FixedEps(CVAEPainter.synthetic(tile_size=tile, seed=4, precision=precision, max_batch=16)),
+                           batch=16, **args)
+    ref = ps.process_SLICS(_OraclePainter(tile, 4), backend=so.NumpyBackend(), **args)
+    assert [p.shape for p in dev] == [(96, 96), (147, 147)]
+    for d, r in zip(dev, ref):
+        assert rel_l2(d, r) <= tol
+    # projected map
+    cosmo = ps.FlatLCDM()
+    yd = ps.create_y_map(dev, [0.21, 0.52], 64, 10.0, cosmo, verbose=False)
+    yr = ps.create_y_map(ref, [0.21, 0.52], 64, 10.0, cosmo, verbose=False)
+    assert rel_l2(yd, yr) <= tol
