@@ -274,6 +274,7 @@ static int check_device(int device) {
 }
 
 static int v2_build(bp_net* net);
+static int v2_build_cgan(bp_net* net);
 
 static int finish_create(bp_net* net) {
   const size_t HW = (size_t)net->H * net->W;
@@ -341,8 +342,8 @@ static int finish_create(bp_net* net) {
           if (!all) for (size_t q = i; q <= j; ++q) { tc_free_layer(&L[q]); win_free_layer(&L[q]); }
         }
     }
-    if (net->kind == NET_CVAE && !getenv("BP_ENGINE_V1")) {
-      int rc = v2_build(net);
+    if (!getenv("BP_ENGINE_V1")) {
+      int rc = net->kind == NET_CVAE ? v2_build(net) : v2_build_cgan(net);
       if (rc != BP_OK) return rc;
     }
   }
@@ -375,7 +376,11 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
                         int* last_act) {
   V2Plan& P = net->v2;
   const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
-  if (caller_out) seq.back().w = false;
+  // the caller's fp32 tiles come from the tail stencil (1 -> 1 convolution) or, for a wider last layer, from its
+  // window GEMM (fp32 plane) followed by an identity tail that applies the inverse transform
+  const bool wide_tail = caller_out && seq.back().w && seq.back().l->d.cout == 1 && seq.back().l->d.cin > 1 &&
+                         !getenv("BP_V2_NOTAIL");
+  if (caller_out && !wide_tail) seq.back().w = false;
   for (size_t i = 0; i < seq.size(); ++i)
     if (seq[i].l->d.res == BP_RES_OPEN) {
       size_t j = i;
@@ -425,6 +430,14 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       if (rc != BP_OK) return rc;
       ops.push_back(op);
       cur = op.out;
+      if (last && wide_tail) {
+        V2Op t;
+        t.kind = V2_TAIL; t.stack = -1; t.index = -1; t.in = cur; t.final = true;
+        TailParams& tp = P.tail;
+        memset(&tp, 0, sizeof(tp));
+        tp.k = 1; tp.w[0] = 1.f; tp.scale = 1.f; tp.shift = 0.f; tp.act = BP_ACT_NONE;
+        ops.push_back(t);
+      }
     } else {
       if (!P.acts[cur].f32) {
         ActDesc a; a.C = d.cin; a.Cp = d.cin; a.H = r.l->H; a.W = r.l->W; a.f32 = true;
@@ -467,6 +480,25 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
     cur = cv.out;
   }
   if (last_act) *last_act = cur;
+  return BP_OK;
+}
+
+static int v2_build_cgan(bp_net* net) {
+  V2Plan& P = net->v2;
+  std::vector<V2Ref> seq;
+  for (size_t i = 0; i < net->st[ST_GEN].layers.size(); ++i) {
+    V2Ref r{ST_GEN, (int)i, &net->st[ST_GEN].layers[i], false, 1};
+    r.w = v2_eligible(*r.l, &r.need_b);
+    seq.push_back(r);
+  }
+  if (!seq[0].w || net->in_c != 2) return BP_OK;           // first layer not lowerable: keep the fp32-bridged engine
+  // generator input [x', z - 1] written straight into the first layer's NHWC layout by the front kernel
+  ActDesc a; a.C = 2; a.Cp = 4; a.H = net->H; a.W = net->W; a.b = seq[0].need_b;
+  int rc = v2_new_act(net, a, &P.dec_in);
+  if (rc != BP_OK) return rc;
+  rc = v2_build_seq(net, seq, P.dec_in, P.ops, true, nullptr);
+  if (rc != BP_OK) return rc;
+  P.built = true;
   return BP_OK;
 }
 
@@ -892,6 +924,21 @@ static int cgan_paint_device(bp_net* net, const float* tiles, const bp_transform
   if (net->debug) net->dbg_n = std::min(n, net->chunk);
   for (int c0 = 0; c0 < n; c0 += net->chunk) {
     const int nb = std::min(net->chunk, n - c0);
+    if (net->v2.built) {
+      PostOp post2;
+      if (flags & BP_FLAG_INVERSE) {
+        post2.post = POST_INV_SHIFT_LOG; post2.sigma = net->params + mb + c0;
+        post2.k = tp->k_out; post2.shift = tp->shift_out;
+      }
+      rc = launch_front_prior(tiles + (size_t)c0 * HW, net->v2.acts[net->v2.dec_in], net->params + c0,
+                              net->params + 2 * mb + c0, tp->k_in, tp->shift_in, (flags & BP_FLAG_TRANSFORM) ? 1 : 0, nb,
+                              net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16, s);
+      if (rc != BP_OK) return rc;
+      rc = v2_run(net, net->v2.ops, out + (size_t)c0 * HW, (long long)HW, post2, nb, s);
+      if (rc != BP_OK) return rc;
+      if (net->debug) break;
+      continue;
+    }
     rc = launch_prepare(tiles + (size_t)c0 * HW, net->in_cat, 2 * (long long)HW, 0, 1, net->params + c0,
                         net->params + 2 * mb + c0, tp->k_in, tp->shift_in, (flags & BP_FLAG_TRANSFORM) ? 1 : 0, nb,
                         (int)HW, s);

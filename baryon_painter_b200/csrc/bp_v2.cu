@@ -32,16 +32,19 @@ bool v2_eligible(const Layer& l, int* need_b) {
   if (d.cout < 8 && !(d.kind == BP_CONV && d.stride == 1 && (d.cout == 1 || d.cout == 2 || d.cout == 4))) return false;
   if (d.kind == BP_CONV) {
     if (d.stride == 1) return d.kernel == 2 * d.pad + 1;   // unit / packing chosen by v2_candidates
-    if (d.kernel != 2 * d.stride || d.pad * 2 != d.stride) return false;
+    // k <= 2s with p = s/2 embeds into the k = 2s family (zero-padded kernel): k4s2p1, k8s4p2, k3s2p1
+    if (d.kernel > 2 * d.stride || d.pad * 2 != d.stride) return false;
     if ((d.stride & (d.stride - 1)) != 0) return false;
     if (l.H % d.stride || l.W % d.stride) return false;
+    if (l.OHF != l.H / d.stride || l.OWF != l.W / d.stride) return false;
     const int cs = v2_padc(d.cin) * d.stride * d.stride;
     if (cs % 16 != 0 || !(cs * 2 <= 128 || (cs * 2) % 128 == 0)) return false;
     *need_b = d.stride;
     return true;
   }
   // transposed
-  if (d.kernel != 2 * d.stride || d.pad * 2 != d.stride || d.out_pad != 0) return false;
+  // k <= 2s, p = s/2, output_padding = 2s - k (output = s * input): k4s2p1, k3s2p1 with output_padding 1
+  if (d.kernel > 2 * d.stride || d.pad * 2 != d.stride || d.out_pad != 2 * d.stride - d.kernel) return false;
   return d.cin % 16 == 0 && (d.cin * 2 <= 128 || (d.cin * 2) % 128 == 0);
 }
 
@@ -94,18 +97,21 @@ int v2_make_spec(const Layer& l, int fmt, WSpec* sp) {
       const int sub = elem / Cp, c = elem % Cp;
       if (sub >= s * s || c >= cin) return 0.f;
       const int sy = sub / s, sx = sub % s;
-      return w[(((size_t)n * cin + c) * k + (a * s + sy)) * k + (b * s + sx)] * sc[n];
+      const int r = a * s + sy, q = b * s + sx;
+      if (r >= k || q >= k) return 0.f;                       // kernel zero-padded to 2s x 2s
+      return w[(((size_t)n * cin + c) * k + r) * k + q] * sc[n];
     };
     return BP_OK;
   }
   // transposed convolution: phase (ph, pw) of output pixel (s*y + ph, s*x + pw)
+  // every phase gets the full 2 x 2 tap grid of the k = 2s family; taps beyond a shorter kernel carry zero weights
   struct PTap { int dy, dx, r, q; };
   std::vector<std::vector<PTap>> ptaps(l.nphase);
   for (int pi = 0; pi < l.nphase; ++pi) {
     const int ph = l.phase[pi].ph, pw = l.phase[pi].pw;
     const int r0 = (ph + p) % s, qh = (ph + p) / s, c0 = (pw + p) % s, qw = (pw + p) / s;
-    for (int aa = 0; r0 + s * aa < k; ++aa)
-      for (int bb = 0; c0 + s * bb < k; ++bb) ptaps[pi].push_back({qh - aa, qw - bb, r0 + s * aa, c0 + s * bb});
+    for (int aa = 0; aa < 2; ++aa)
+      for (int bb = 0; bb < 2; ++bb) ptaps[pi].push_back({qh - aa, qw - bb, r0 + s * aa, c0 + s * bb});
   }
   sp->OHl = l.H; sp->OWl = l.W;
   sp->ry = sp->rx = s;
@@ -133,7 +139,7 @@ int v2_make_spec(const Layer& l, int fmt, WSpec* sp) {
       if (pi >= nph || co >= cout || elem >= cin) return 0.f;
       for (const PTap& pt : ptaps[pi])
         if (pt.dy == all[t].dl && pt.dx == all[t].du)
-          return w[(((size_t)elem * cout + co) * k + pt.r) * k + pt.q] * sc[co];
+          return (pt.r < k && pt.q < k) ? w[(((size_t)elem * cout + co) * k + pt.r) * k + pt.q] * sc[co] : 0.f;
       return 0.f;
     };
     return BP_OK;
@@ -150,6 +156,7 @@ int v2_make_spec(const Layer& l, int fmt, WSpec* sp) {
   sp->weight = [=, &w, &sc](int pi, int t, int elem, int n) -> float {
     if (n >= cout || elem >= cin) return 0.f;
     const PTap& pt = ptaps[pi][t];
+    if (pt.r >= k || pt.q >= k) return 0.f;
     return w[(((size_t)elem * cout + n) * k + pt.r) * k + pt.q] * sc[n];
   };
   return BP_OK;
@@ -222,7 +229,6 @@ int v2_candidates(const Layer& l, int fmt, int Cp, std::vector<WSpec>* out) {
     const int ub = G * Cp * 2;
     if (!(ub == 32 || ub == 64 || ub == 128 || (G == 1 && ub % 128 == 0))) continue;
     if (l.OWF % G) continue;
-    if (d.cout == 1 && G < 4) continue;            // fp32 plane output is written in float4 quads
     for (int Jy : {1, 2, 4, 8, 16}) {
       const int N = std::max(16, Jy * G * coutp);
       if (N > 128) continue;

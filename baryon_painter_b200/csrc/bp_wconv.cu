@@ -350,8 +350,10 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
           rbase = (((long long)R.n * a.OH + y0) * a.OW + x0) * a.oC;
         } else {
           const int Hs = a.OH / ob + 1, Ws = a.OW / ob + 1;
-          if (a.row_sy) {
+          if (a.row_sy > 0) {
             rbase = ((((long long)R.n * Hs + (long long)Rl * a.row_sy) * Ws + (long long)U * a.row_sx) * ob * ob) * a.oC;
+          } else if (a.row_sy < 0) {
+            rbase = 0;                       // blocks not aligned to the space-to-depth grid: full address per segment
           } else {
             const int yy = y0 + (ob >> 1), xx = x0 + (ob >> 1);
             const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
@@ -390,7 +392,20 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
             tmem_ld_wait();
           }
           const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
-          if (OUTF32) {
+          if (OUTF32 && a.seg_shift < 2) {
+            // fp32 plane, segments of 1 or 2 pixels (wide-input layers packed with G < 4): scalar stores
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int n0 = c0 + e;
+              const int sg = n0 >> a.seg_shift, ch = n0 & seg_mask;
+              if (ch >= a.seg_valid || sg >= P.nseg) continue;
+              const int seg = P.seg_begin + sg;
+              if (!valid || (a.dbg & 2)) continue;
+              if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
+              reinterpret_cast<float*>(a.out)[rbase + a.seg_delta[seg] + ch] =
+                  w_act<ACT>(__uint_as_float(v[e]) + s_shift[n0], a.act, a.act_param);
+            }
+          } else if (OUTF32) {
             // fp32 output (single channel plane): segments of >= 4 columns, one float4 per quad
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -440,7 +455,14 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               uint4 o;
               o.x = w_pack16<ACT>(xv[0], xv[1], a.fmt); o.y = w_pack16<ACT>(xv[2], xv[3], a.fmt);
               o.z = w_pack16<ACT>(xv[4], xv[5], a.fmt); o.w = w_pack16<ACT>(xv[6], xv[7], a.fmt);
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + (rbase + a.seg_delta[seg] + ch)) = o;
+              long long off = rbase + a.seg_delta[seg] + ch;
+              if (a.row_sy < 0) {
+                const int Hs = a.OH / ob + 1, Ws = a.OW / ob + 1;
+                const int yy = y0 + a.seg_oy[seg] + (ob >> 1), xx = x0 + a.seg_ox[seg] + (ob >> 1);
+                const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
+                off = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * a.oC + ch;
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + off) = o;
             }
           }
           if (SKIP) {
@@ -532,7 +554,7 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
     BP_REQUIRE(unit_bytes % 128 == 0, BP_E_UNSUPPORTED, "window GEMM: unit of %d bytes", unit_bytes);
   }
   BP_REQUIRE(sp.N >= 16 && sp.N <= 256 && sp.N % 16 == 0, BP_E_UNSUPPORTED, "window GEMM: N=%d", sp.N);
-  BP_REQUIRE((sp.seg_len & (sp.seg_len - 1)) == 0 && sp.seg_len >= 4, BP_E_UNSUPPORTED, "segment length %d", sp.seg_len);
+  BP_REQUIRE((sp.seg_len & (sp.seg_len - 1)) == 0 && sp.seg_len >= 1, BP_E_UNSUPPORTED, "segment length %d", sp.seg_len);
   const int kpu = UB / 32;
 
   // ---- tap grids: every phase's taps must form a full rectangle (true for all lowerings in bp_v2.cu)
@@ -782,19 +804,19 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
     const int b = out.b, pd = b >> 1;
     a.row_sy = a.row_sx = 0;
     if (b > 1 && !(a.ry == 1 && a.rx == 1)) {
-      BP_REQUIRE(a.ry % b == 0 && a.rx % b == 0 && !out.f32, BP_E_UNSUPPORTED,
-                 "window GEMM: %dx%d output blocks into a space-to-depth %d layout", a.ry, a.rx, b);
-      a.row_sy = a.ry / b; a.row_sx = a.rx / b;
+      BP_REQUIRE(!out.f32, BP_E_UNSUPPORTED, "window GEMM: fp32 output into a space-to-depth layout");
+      if (a.ry % b == 0 && a.rx % b == 0) { a.row_sy = a.ry / b; a.row_sx = a.rx / b; }
+      else a.row_sy = a.row_sx = -1;       // general per-segment addressing
     }
     const long long Ws = out.Ws();
     for (size_t i = 0; i < wl->segs.size(); ++i) {
       const int oy = wl->segs[i].x, ox = wl->segs[i].y;
       a.seg_oy[i] = oy; a.seg_ox[i] = ox;
       if (b == 1) a.seg_delta[i] = ((long long)oy * out.W + ox) * a.oC;
-      else if (a.row_sy) a.seg_delta[i] = (((long long)((oy + pd) / b) * Ws + (ox + pd) / b) * b * b + ((oy + pd) % b) * b + (ox + pd) % b) * a.oC;
+      else if (a.row_sy > 0) a.seg_delta[i] = (((long long)((oy + pd) / b) * Ws + (ox + pd) / b) * b * b + ((oy + pd) % b) * b + (ox + pd) % b) * a.oC;
       else a.seg_delta[i] = 0;
     }
-    if (b > 1 && !a.row_sy) BP_REQUIRE(wl->segs.size() == 1 && wl->segs[0].x == 0 && wl->segs[0].y == 0, BP_E_UNSUPPORTED,
+    if (b > 1 && a.row_sy == 0) BP_REQUIRE(wl->segs.size() == 1 && wl->segs[0].x == 0 && wl->segs[0].y == 0, BP_E_UNSUPPORTED,
                                      "window GEMM: segmented output into a space-to-depth layout");
   }
   const int grid = std::min(a.total_regions, g_w_sms);
