@@ -116,7 +116,11 @@ if __name__ == "__main__":
         npx = int(args.synthetic_plane_pixels)
 
         def plane_source(i, kind):
-            return np.random.default_rng(100 + i).lognormal(-0.5, 1.0, (npx, npx)).astype(np.float32)
+            # smooth, strictly positive log-normal density (mean ~1): a cubic-spline zoom of white noise would
+            # overshoot below zero and the shift-log transform would see negative densities
+            import scipy.ndimage
+            g = scipy.ndimage.gaussian_filter(np.random.default_rng(100 + i).standard_normal((npx, npx)), 3.0, mode="wrap")
+            return np.exp(g / g.std() - 0.5).astype(np.float32)
     else:
         SLICS_base_path = args.SLICS_base_path
         LOS = int(args.SLICS_LOS)
