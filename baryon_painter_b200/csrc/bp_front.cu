@@ -25,8 +25,21 @@ __device__ __forceinline__ uint16_t f_to16(float v, int fmt) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
-__device__ __forceinline__ float f_transform(float x, float sigma, float k, float shift, int on) {
-  return on ? logf(x / sigma + 1.f) / k - shift : x;
+// forward transform; these kernels only feed the 16-bit path, so the fast log (2 ulp) is ample
+__device__ __forceinline__ float f_transform(float x, float inv_sigma, float inv_k, float shift, int on) {
+  return on ? __logf(fmaf(x, inv_sigma, 1.f)) * inv_k - shift : x;
+}
+
+__device__ __forceinline__ float f_act(float v, int act, float p) {
+  switch (act) {
+    case BP_ACT_RELU: return fmaxf(v, 0.f);
+    case BP_ACT_LEAKY:
+    case BP_ACT_PRELU: return v >= 0.f ? v : v * p;
+    case BP_ACT_SOFTPLUS: return v > 20.f ? v : log1pf(expf(v));
+    case BP_ACT_TANH: return tanhf(v);
+    case BP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
 }
 
 // ---- prior input: [y, z, 0, 0] per pixel, space-to-depth block 2 (pixel (y,x) -> block ((y+1)/2, (x+1)/2)) ----
@@ -34,13 +47,13 @@ __global__ void front_prior_kernel(const float* __restrict__ tiles, uint2* __res
                                    const float* __restrict__ aux, float k_in, float shift_in, int do_t, int H, int W, int b,
                                    int fmt) {
   const int n = blockIdx.z;
-  const float sg = do_t ? sigma[n] : 1.f;
+  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
   const uint16_t z16 = f_to16(aux[n], fmt);
   const int hw = H * W;
   const int Hs = b > 1 ? H / b + 1 : H, Ws = b > 1 ? W / b + 1 : W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
     const int y = p / W, x = p - y * W;
-    const float v = f_transform(tiles[(size_t)n * hw + p], sg, k_in, shift_in, do_t);
+    const float v = f_transform(tiles[(size_t)n * hw + p], sg, ik, shift_in, do_t);
     size_t o;
     if (b == 1) {
       o = (size_t)n * hw + p;
@@ -65,6 +78,83 @@ int launch_front_prior(const float* tiles, const ActDesc& out, const float* sigm
   return BP_OK;
 }
 
+// ---- prior input fused with prior_network.0 (k4 s2 p1, 2 -> <= 8 channels, BN + activation) -----------------
+// CTA = 32 x 32 output pixels: the 66 x 66 window of raw densities is transformed once into shared memory,
+// every thread produces 4 output pixels x 8 channels (FFMA, weights in the constant bank) and writes 16 bytes
+// per pixel into the layout the next layer reads.  The constant z plane contributes z * (sum of the in-image
+// taps' weights); only the border outputs see fewer taps.
+__global__ void __launch_bounds__(256) front_prior_conv_kernel(const float* __restrict__ tiles, uint16_t* __restrict__ out,
+                                                               const float* __restrict__ sigma, const float* __restrict__ aux,
+                                                               const FrontConvParams fc, float k_in, float shift_in, int do_t,
+                                                               int H, int W, int ob, int oCp, int fmt) {
+  __shared__ float sy[66][67];
+  const int n = blockIdx.z;
+  const int OH = H >> 1, OW = W >> 1;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
+  const float z = aux[n];
+  const float* src = tiles + (size_t)n * H * W;
+  for (int t = threadIdx.x; t < 66 * 66; t += blockDim.x) {
+    const int ly = t / 66, lx = t - ly * 66;
+    const int y = 2 * i0 - 1 + ly, x = 2 * j0 - 1 + lx;
+    sy[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? f_transform(__ldg(src + (size_t)y * W + x), sg, ik, shift_in, do_t) : 0.f;
+  }
+  __syncthreads();
+  const int lj = threadIdx.x & 31, li0 = (threadIdx.x >> 5) * 4;
+  const int j = j0 + lj;
+  if (j >= OW) return;
+#pragma unroll 1
+  for (int r4 = 0; r4 < 4; ++r4) {
+    const int li = li0 + r4, i = i0 + li;
+    if (i >= OH) break;
+    float acc[8];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const bool rin = !(i == 0 && r == 0) && !(i == OH - 1 && r == 3);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool cin_ = !(j == 0 && q == 0) && !(j == OW - 1 && q == 3);
+        const float yv = sy[2 * li + r][2 * lj + q];
+        const float zv = (rin && cin_) ? z : 0.f;
+#pragma unroll
+        for (int co = 0; co < 8; ++co) acc[co] = fmaf(yv, fc.w[co][0][r * 4 + q], fmaf(zv, fc.w[co][1][r * 4 + q], acc[co]));
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int c2 = 0; c2 < 4; ++c2) {
+      const float a0 = f_act(acc[2 * c2] + fc.shift[2 * c2], fc.act, fc.act_param);
+      const float a1 = f_act(acc[2 * c2 + 1] + fc.shift[2 * c2 + 1], fc.act, fc.act_param);
+      pk[c2] = (uint32_t)f_to16(2 * c2 < fc.cout ? a0 : 0.f, fmt) | ((uint32_t)f_to16(2 * c2 + 1 < fc.cout ? a1 : 0.f, fmt) << 16);
+    }
+    size_t o;
+    if (ob == 1) {
+      o = (((size_t)n * OH + i) * OW + j) * (size_t)oCp;
+    } else {
+      const int yy = i + (ob >> 1), xx = j + (ob >> 1);
+      const int by = yy / ob, sy_ = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
+      const int Hs = OH / ob + 1, Ws = OW / ob + 1;
+      o = (((((size_t)n * Hs + by) * Ws + bx) * ob + sy_) * ob + sx) * (size_t)oCp;
+    }
+    *reinterpret_cast<uint4*>(out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+int launch_front_prior_conv(const float* tiles, const ActDesc& out, const float* sigma, const float* aux,
+                            const FrontConvParams& fc, float k_in, float shift_in, int do_transform, int H, int W, int nb,
+                            int fmt, cudaStream_t s) {
+  BP_REQUIRE(!out.f32 && out.Cp == 8 && out.H == H / 2 && out.W == W / 2 && (H % 2) == 0 && (W % 2) == 0, BP_E_INVALID,
+             "front_prior_conv: bad output tensor");
+  const dim3 grid((out.W + 31) / 32, (out.H + 31) / 32, nb);
+  front_prior_conv_kernel<<<grid, 256, 0, s>>>(tiles, static_cast<uint16_t*>(out.ptr), sigma, aux, fc, k_in, shift_in,
+                                               do_transform, H, W, out.b, out.Cp, fmt);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
 // ---- decoder input ---------------------------------------------------------------------------------
 // 1 -> 1 channel transposed convolution with k = 2s, p = s/2: two taps per dimension
 __device__ __forceinline__ float up_at(const float* in, int ih, int iw, const float* w, int k, int s, int p, int oy, int ox) {
@@ -82,17 +172,6 @@ __device__ __forceinline__ float up_at(const float* in, int ih, int iw, const fl
     }
   }
   return acc;
-}
-__device__ __forceinline__ float f_act(float v, int act, float p) {
-  switch (act) {
-    case BP_ACT_RELU: return fmaxf(v, 0.f);
-    case BP_ACT_LEAKY:
-    case BP_ACT_PRELU: return v >= 0.f ? v : v * p;
-    case BP_ACT_SOFTPLUS: return v > 20.f ? v : log1pf(expf(v));
-    case BP_ACT_TANH: return tanhf(v);
-    case BP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    default: return v;
-  }
 }
 
 // one CTA = one band of `rows` output rows of one tile.  Levels 0 .. nl-2 of the pyramid are recomputed per CTA
@@ -136,16 +215,38 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
     __syncthreads();
   }
   const int L = pz.nl - 1;
-  const float sg = do_t ? sigma[n] : 1.f;
-  const uint16_t z16 = f_to16(aux[n], fmt);
+  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
+  const uint32_t z16 = f_to16(aux[n], fmt);
   const int nr = hi[pz.nl] - lo[pz.nl] + 1;
+  const float* src = buf[L] - (size_t)lo[L] * lvw[L];
+  if ((W & 3) == 0) {
+    // four pixels per thread: one 16-byte tile load, two 16-byte NHWC stores
+    const int W4 = W >> 2;
+    for (int i = threadIdx.x; i < nr * W4; i += blockDim.x) {
+      const int oy = y0 + i / W4, ox = (i % W4) * 4;
+      const size_t p = ((size_t)n * H + oy) * W + ox;
+      const float4 t = __ldg(reinterpret_cast<const float4*>(tiles + p));
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+      uint32_t lo16[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = up_at(src, hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], pz.p[L], oy, ox + e);
+        v = f_act(fmaf(v, pz.scale[L], pz.shift[L]), pz.act[L], pz.act_param[L]);
+        lo16[e] = (uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(f_transform(tv[e], sg, ik, shift_in, do_t), fmt) << 16);
+      }
+      uint4* o = reinterpret_cast<uint4*>(out + p);
+      o[0] = make_uint4(lo16[0], z16, lo16[1], z16);
+      o[1] = make_uint4(lo16[2], z16, lo16[3], z16);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < nr * W; i += blockDim.x) {
     const int oy = y0 + i / W, ox = i % W;
-    float v = up_at(buf[L] - (size_t)lo[L] * lvw[L], hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], pz.p[L], oy, ox);
+    float v = up_at(src, hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], pz.p[L], oy, ox);
     v = f_act(fmaf(v, pz.scale[L], pz.shift[L]), pz.act[L], pz.act_param[L]);
     const size_t p = ((size_t)n * H + oy) * W + ox;
-    const float yv = f_transform(tiles[p], sg, k_in, shift_in, do_t);
-    out[p] = make_uint2((uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(yv, fmt) << 16), (uint32_t)z16);
+    const float yv = f_transform(tiles[p], sg, ik, shift_in, do_t);
+    out[p] = make_uint2((uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(yv, fmt) << 16), z16);
   }
 }
 
@@ -213,8 +314,11 @@ __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restri
   float o[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    float v = f_act(fmaf(acc[e], tp.scale, tp.shift), tp.act, tp.act_param);
-    if (tp.post) v = (expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+    float v = fmaf(acc[e], tp.scale, tp.shift);
+    // 16-bit path only: fast exp / log (a few ulp) are far below its tolerance
+    if (tp.act == BP_ACT_SOFTPLUS) v = v > 20.f ? v : __logf(1.f + __expf(v));
+    else v = f_act(v, tp.act, tp.act_param);
+    if (tp.post) v = (__expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
     o[e] = v;
   }
   float* dst = out + (size_t)n * out_bs + (size_t)y * W + x0 + tx;

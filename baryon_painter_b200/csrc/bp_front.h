@@ -28,6 +28,17 @@ struct TailParams {
   float post_k, post_shift;
 };
 
+// prior_network.0 fused into the front pass: k4 s2 p1 convolution of the 2-channel [y, z] input to <= 8 channels
+struct FrontConvParams {
+  int cout, act;
+  float act_param;
+  float w[8][2][16];          // [co][ci][r*4 + q], BN scale folded in
+  float shift[8];
+};
+
+int launch_front_prior_conv(const float* tiles, const ActDesc& out, const float* sigma, const float* aux,
+                            const FrontConvParams& fc, float k_in, float shift_in, int do_transform, int H, int W, int nb,
+                            int fmt, cudaStream_t s);
 int launch_front_prior(const float* tiles, const ActDesc& out, const float* sigma, const float* aux, float k_in,
                        float shift_in, int do_transform, int nb, int fmt, cudaStream_t s);
 int launch_front_latent(const float* tiles, const float* latent, const ActDesc& out, const float* sigma, const float* aux,

@@ -168,6 +168,8 @@ struct V2Plan {
   int dec_in = -1, prior_in = -1, prior_out = -1;
   PzParams pz;
   TailParams tail;
+  bool prior_conv0 = false;       // prior_network.0 runs inside the front kernel
+  FrontConvParams fc;
 };
 
 struct bp_net {
@@ -286,7 +288,7 @@ static int finish_create(bp_net* net) {
   }
   // chunk: keep the three rotating activation buffers of one chunk around L2 size (126 MB) so that
   // a layer's output is still cache-resident when the next layer reads it
-  int chunk = net->prec == BP_PREC_F32 ? 4 : 64;
+  int chunk = net->prec == BP_PREC_F32 ? 4 : 256;
   if (const char* e = getenv("BP_CHUNK")) chunk = std::max(1, atoi(e));
   net->chunk = std::min(chunk, net->max_batch);
   net->pool_floats = mx * net->chunk;
@@ -552,9 +554,30 @@ static int v2_build(bp_net* net) {
       ps.push_back(r);
     }
     if (ps[0].w && prl[0].d.cin == 2) {
-      ActDesc a; a.C = 2; a.Cp = 4; a.H = net->H; a.W = net->W; a.b = ps[0].need_b;
-      rc = v2_new_act(net, a, &P.prior_in);
-      if (rc != BP_OK) return rc;
+      const bp_layer_desc& d0 = prl[0].d;
+      // k4 s2 p1, 2 -> <= 8 channels followed by another window GEMM: folded into the front pass (FFMA stencil)
+      const bool fuse0 = d0.kind == BP_CONV && d0.kernel == 4 && d0.stride == 2 && d0.pad == 1 && d0.cout <= 8 &&
+                         d0.res == BP_RES_NONE && ps.size() > 1 && ps[1].w && (net->H % 2) == 0 && (net->W % 2) == 0 &&
+                         !getenv("BP_V2_NOFUSE0");
+      if (fuse0) {
+        memset(&P.fc, 0, sizeof(P.fc));
+        P.fc.cout = d0.cout; P.fc.act = d0.act; P.fc.act_param = d0.act_param;
+        for (int co = 0; co < d0.cout; ++co) {
+          P.fc.shift[co] = prl[0].host_shift[co];
+          for (int ci = 0; ci < 2; ++ci)
+            for (int t = 0; t < 16; ++t) P.fc.w[co][ci][t] = prl[0].host_weight[((size_t)co * 2 + ci) * 16 + t] * prl[0].host_scale[co];
+        }
+        ActDesc a; a.C = d0.cout; a.Cp = 8; a.H = net->H / 2; a.W = net->W / 2; a.b = ps[1].need_b;
+        rc = v2_new_act(net, a, &P.prior_in);
+        if (rc != BP_OK) return rc;
+        ps.erase(ps.begin());
+        P.prior_conv0 = true;
+        prl[0].v2 = true;
+      } else {
+        ActDesc a; a.C = 2; a.Cp = 4; a.H = net->H; a.W = net->W; a.b = ps[0].need_b;
+        rc = v2_new_act(net, a, &P.prior_in);
+        if (rc != BP_OK) return rc;
+      }
       rc = v2_build_seq(net, ps, P.prior_in, P.prior_ops, false, &P.prior_out);
       if (rc != BP_OK) return rc;
       BP_REQUIRE(P.acts[P.prior_out].f32, BP_E_INVALID, "internal: prior head is not fp32");
@@ -802,9 +825,23 @@ static int cvae_chunk_front(bp_net* net, const float* tiles, const bp_transform_
   if (!need_prior) return BP_OK;
   PostOp none;
   if (v2_prior) {
-    rc = launch_front_prior(tiles + (size_t)c0 * HW, P.acts[P.prior_in], net->params + c0, net->params + 2 * mb + c0,
-                            tp->k_in, tp->shift_in, do_t, nb, fmt, s);
+    if (P.prior_conv0)
+      rc = launch_front_prior_conv(tiles + (size_t)c0 * HW, P.acts[P.prior_in], net->params + c0, net->params + 2 * mb + c0,
+                                   P.fc, tp->k_in, tp->shift_in, do_t, net->H, net->W, nb, fmt, s);
+    else
+      rc = launch_front_prior(tiles + (size_t)c0 * HW, P.acts[P.prior_in], net->params + c0, net->params + 2 * mb + c0,
+                              tp->k_in, tp->shift_in, do_t, nb, fmt, s);
     if (rc != BP_OK) return rc;
+    if (net->debug && P.prior_conv0) {
+      // record the fused kernel's own output as the activation of prior_network layer 0
+      const Layer& l0 = net->st[ST_PRIOR].layers[0];
+      const size_t per = (size_t)l0.d.cout * l0.OHF * l0.OWF;
+      std::vector<float*>& dv = net->dbg[ST_PRIOR];
+      if (dv.size() < net->st[ST_PRIOR].layers.size()) dv.resize(net->st[ST_PRIOR].layers.size(), nullptr);
+      if (!dv[0]) BP_CUDA_TRY(cudaMalloc(&dv[0], sizeof(float) * per * net->chunk));
+      rc = launch_nhwc16_to_nchw32(P.acts[P.prior_in], dv[0], (long long)per, nb, fmt, s);
+      if (rc != BP_OK) return rc;
+    }
     rc = v2_run(net, P.prior_ops, nullptr, 0, none, nb, s);
     if (rc != BP_OK) return rc;
     *prior_out = static_cast<float*>(P.acts[P.prior_out].ptr);

@@ -110,6 +110,18 @@ __device__ __forceinline__ float2 w_unpack16(uint32_t u, int fmt) {
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane instead of two half-sector pieces
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+
 struct WRegion {
   int pi, n, strip, rr;
   int l0;        // M-domain line whose window starts the patch (patch line 0 = input line l0*Jy - top)
@@ -430,10 +442,14 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               }
             }
           } else {
+            uint4 o[2];
+            long long offs[2];
+            bool ok[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int n0 = c0 + h * 8;
               const int seg = P.seg_begin + (n0 >> a.seg_shift), ch = n0 & seg_mask;
+              ok[h] = false;
               if (ch >= a.seg_valid || (n0 >> a.seg_shift) >= P.nseg) continue;   // warp-uniform
               if (!valid || (a.dbg & 2)) continue;
               if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
@@ -452,9 +468,8 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e) xv[e] = w_act<ACT>(xv[e], a.act, a.act_param);
-              uint4 o;
-              o.x = w_pack16<ACT>(xv[0], xv[1], a.fmt); o.y = w_pack16<ACT>(xv[2], xv[3], a.fmt);
-              o.z = w_pack16<ACT>(xv[4], xv[5], a.fmt); o.w = w_pack16<ACT>(xv[6], xv[7], a.fmt);
+              o[h].x = w_pack16<ACT>(xv[0], xv[1], a.fmt); o[h].y = w_pack16<ACT>(xv[2], xv[3], a.fmt);
+              o[h].z = w_pack16<ACT>(xv[4], xv[5], a.fmt); o[h].w = w_pack16<ACT>(xv[6], xv[7], a.fmt);
               long long off = rbase + a.seg_delta[seg] + ch;
               if (a.row_sy < 0) {
                 const int Hs = a.OH / ob + 1, Ws = a.OW / ob + 1;
@@ -462,7 +477,15 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
                 const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
                 off = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * a.oC + ch;
               }
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + off) = o;
+              offs[h] = off;
+              ok[h] = true;
+            }
+            uint16_t* ob16 = reinterpret_cast<uint16_t*>(a.out);
+            if (a.seg_shift >= 4 && ok[0] && ok[1]) {
+              st_global_v8(ob16 + offs[0], o[0], o[1]);              // both halves in one segment: 32 contiguous bytes
+            } else {
+              if (ok[0]) *reinterpret_cast<uint4*>(ob16 + offs[0]) = o[0];
+              if (ok[1]) *reinterpret_cast<uint4*>(ob16 + offs[1]) = o[1];
             }
           }
           if (SKIP) {
