@@ -903,6 +903,7 @@ static int cvae_chunk_back(bp_net* net, const float* tiles, const float* latent,
 struct ChunkHooks {
   std::vector<cudaEvent_t>* ready = nullptr;
   std::vector<cudaEvent_t>* done = nullptr;
+  int step = 0;       // tiles per pipeline chunk (<= the plan's chunk capacity); 0 = the plan's chunk
 };
 
 static int cvae_paint_device(bp_net* net, const float* tiles, const float* latent, int mode, uint64_t seed,
@@ -922,10 +923,11 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
   const size_t lhw = (size_t)net->lh * net->lw;
   net->prior_valid = 0;
   if (net->debug) net->dbg_n = std::min(n, net->chunk);
-  for (int c0 = 0; c0 < n; c0 += net->chunk) {
-    const int nb = std::min(net->chunk, n - c0);
+  const int step = (hooks && hooks->step > 0) ? std::min(hooks->step, net->chunk) : net->chunk;
+  for (int c0 = 0; c0 < n; c0 += step) {
+    const int nb = std::min(step, n - c0);
     float* prior_out = nullptr;
-    if (hooks && hooks->ready) BP_CUDA_TRY(cudaStreamWaitEvent(s, (*hooks->ready)[c0 / net->chunk], 0));
+    if (hooks && hooks->ready) BP_CUDA_TRY(cudaStreamWaitEvent(s, (*hooks->ready)[c0 / step], 0));
     rc = cvae_chunk_front(net, tiles, tp, flags, c0, nb, mode != BP_LATENT_GIVEN, s, &prior_out);
     if (rc != BP_OK) return rc;
     const float* lat;
@@ -940,7 +942,7 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
     }
     rc = cvae_chunk_back(net, tiles, lat, tp, flags, c0, nb, out + (size_t)c0 * HW, s);
     if (rc != BP_OK) return rc;
-    if (hooks && hooks->done) BP_CUDA_TRY(cudaEventRecord((*hooks->done)[c0 / net->chunk], s));
+    if (hooks && hooks->done) BP_CUDA_TRY(cudaEventRecord((*hooks->done)[c0 / step], s));
     if (net->debug) break;  // debug buffers hold one chunk
   }
   if (mode != BP_LATENT_GIVEN) net->prior_valid = n;
@@ -1129,7 +1131,11 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   BP_CUDA_TRY(cudaSetDevice(net->device));
   const size_t HW = (size_t)net->H * net->W, lhw = (size_t)net->lh * net->lw;
   cudaStream_t s = net->stream, sin = net->copy_stream, sout = net->out_stream;
-  const int nchunks = (n + net->chunk - 1) / net->chunk;
+  // pipeline granularity: small enough that copy-in / compute / copy-out of neighbouring chunks overlap, large enough
+  // that the kernels still fill the machine (BP_HOST_STEP overrides)
+  static const int env_step = getenv("BP_HOST_STEP") ? atoi(getenv("BP_HOST_STEP")) : 64;
+  const int step = std::max(1, std::min(net->chunk, env_step));
+  const int nchunks = (n + step - 1) / step;
   while ((int)net->ev_ready.size() < nchunks) {
     cudaEvent_t a, b, c;
     BP_CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -1144,7 +1150,7 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   }
   // inputs: chunk by chunk on the copy-in stream (staging a pageable chunk overlaps the device's work on earlier ones)
   for (int c = 0; c < nchunks; ++c) {
-    const size_t c0 = (size_t)c * net->chunk, nb = std::min((size_t)net->chunk, (size_t)n - c0);
+    const size_t c0 = (size_t)c * step, nb = std::min((size_t)step, (size_t)n - c0);
     const float* src = tiles + c0 * HW;
     if (!in_pinned) {
       memcpy(net->h_in + c0 * HW, src, sizeof(float) * HW * nb);
@@ -1154,12 +1160,12 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
     BP_CUDA_TRY(cudaEventRecord(net->ev_ready[c], sin));
   }
   ChunkHooks hooks;
-  hooks.ready = &net->ev_ready; hooks.done = &net->ev_chunk_done;
+  hooks.ready = &net->ev_ready; hooks.done = &net->ev_chunk_done; hooks.step = step;
   int rc = cvae_paint_device(net, net->d_in, net->d_lat, latent_mode, seed, tp, flags, net->d_out, n, s, &hooks);
   if (rc != BP_OK) return rc;
   const int done_chunks = net->debug ? 1 : nchunks;
   for (int c = 0; c < done_chunks; ++c) {
-    const size_t c0 = (size_t)c * net->chunk, nb = std::min((size_t)net->chunk, (size_t)n - c0);
+    const size_t c0 = (size_t)c * step, nb = std::min((size_t)step, (size_t)n - c0);
     float* dst = out_pinned ? out + c0 * HW : net->h_out + c0 * HW;
     BP_CUDA_TRY(cudaStreamWaitEvent(sout, net->ev_chunk_done[c], 0));
     BP_CUDA_TRY(cudaMemcpyAsync(dst, net->d_out + c0 * HW, sizeof(float) * HW * nb, cudaMemcpyDeviceToHost, sout));
@@ -1167,7 +1173,7 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   }
   if (!out_pinned) {
     for (int c = 0; c < done_chunks; ++c) {
-      const size_t c0 = (size_t)c * net->chunk, nb = std::min((size_t)net->chunk, (size_t)n - c0);
+      const size_t c0 = (size_t)c * step, nb = std::min((size_t)step, (size_t)n - c0);
       BP_CUDA_TRY(cudaEventSynchronize(net->ev_out[c]));
       memcpy(out + c0 * HW, net->h_out + c0 * HW, sizeof(float) * HW * nb);
     }
