@@ -93,21 +93,43 @@ __device__ __forceinline__ float w_act(float v, int act, float p) {
     default: return v;
   }
 }
-// two fp32 -> packed 16-bit pair; fp16 saturates to +-65504 (half2 min/max after the conversion)
-template <int ACT>
-__device__ __forceinline__ uint32_t w_pack16(float a, float b, int fmt) {
-  if (fmt == 0) {
-    __half2 h = __floats2half2_rn(a, b);
-    h = __hmin2(h, __half2half2(__ushort_as_half((unsigned short)0x7BFF)));
-    if (ACT != BP_ACT_RELU) h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0xFBFF)));
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+// ---- epilogue arithmetic on column pairs -----------------------------------------------------------
+// acc pair + shift pair (+ residual pair) as packed fp32 adds (FADD2), activation, then one conversion that also
+// saturates to the finite 16-bit range -- and applies ReLU for free (F2FP.SATFINITE.RELU...PACK_AB).
+__device__ __forceinline__ unsigned long long w_pack_b64(uint32_t lo, uint32_t hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
 }
-__device__ __forceinline__ float2 w_unpack16(uint32_t u, int fmt) {
-  if (fmt == 0) return __half22float2(*reinterpret_cast<__half2*>(&u));
-  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+__device__ __forceinline__ unsigned long long w_add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+template <int FMT>
+__device__ __forceinline__ unsigned long long w_unpack16_b64(uint32_t u) {   // packed 16-bit pair -> fp32 pair
+  float2 f;
+  if (FMT == 0) f = __half22float2(*reinterpret_cast<__half2*>(&u));
+  else f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return w_pack_b64(__float_as_uint(f.x), __float_as_uint(f.y));
+}
+template <int ACT, int FMT>
+__device__ __forceinline__ uint32_t w_finish_pair(unsigned long long x2, int act, float p) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(x2));
+  uint32_t r;
+  if (ACT == BP_ACT_RELU) {
+    if (FMT == 0) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+    else asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+    return r;
+  }
+  if (ACT != BP_ACT_NONE) {
+    x = w_act<ACT>(x, act, p);
+    y = w_act<ACT>(y, act, p);
+  }
+  if (FMT == 0) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  return r;
 }
 
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane instead of two half-sector pieces
@@ -234,7 +256,7 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
   }
 }
 
-template <int ACT, bool SKIP, bool OUTF32>
+template <int ACT, bool SKIP, bool OUTF32, int FMT>
 __global__ void __launch_bounds__(W_THREADS, 1)
 wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -331,166 +353,157 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     // ===================== epilogue =====================
     // warp = 4 + e: TMEM lane quarter e % 4 (a warp may only touch lanes 32*(warp % 4) ..), 16-column chunks
     // e / 4, e / 4 + W_EPI_WARPS / 4, ...  One thread = one M row; a chunk's two 8-column halves are 16-byte
-    // stores to row_base + seg_delta[segment] (+ channel).
+    // stores (one 32-byte store when both lie in one segment) to row_base + seg_delta[segment] (+ channel).
     constexpr int NEW = W_EPI_WARPS / 4;
     const int q = warp & 3;
     const int cpart = (warp - 4) >> 2;
     const int m = q * 32 + lane;
-    const int seg_mask = (1 << a.seg_shift) - 1;
-    const int ob = a.ob;
+    const int seg_shift = a.seg_shift, seg_mask = (1 << a.seg_shift) - 1, seg_valid = a.seg_valid;
+    const int ob = a.ob, OH = a.OH, OW = a.OW, oC = a.oC, ry = a.ry, rx = a.rx, T_r = a.T_r;
+    const int act = a.act;
+    const float act_param = a.act_param;
+    uint16_t* const ob16 = reinterpret_cast<uint16_t*>(a.out);
     uint32_t as = 0, apar = 0;
     for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x) {
       const WRegion R = w_decode(a, reg);
       const WPhase P = a.phase[R.pi];
       bool waited = false;
-      for (int mt = 0; mt < a.T_r; ++mt) {
+      for (int mt = 0; mt < T_r; ++mt) {
         int Rl, c;
         if (a.mode == W_LINE) {
           Rl = R.l0 + mt;
           c = m;
         } else {
-          const int f = R.rr * a.T_r * 128 + mt * 128 + m;
+          const int f = R.rr * T_r * 128 + mt * 128 + m;
           Rl = f / a.PW;
           c = f - Rl * a.PW;
         }
         const int U = R.strip * a.Wt + c;
         const bool valid = c < a.Wt && U < a.OWl && Rl < a.OHl;
         // element offset of this row's block and whether any of its pixels can fall outside the image
-        const int y0 = Rl * a.ry, x0 = U * a.rx;
+        const int y0 = Rl * ry, x0 = U * rx;
         long long rbase;
         if (ob == 1) {
-          rbase = (((long long)R.n * a.OH + y0) * a.OW + x0) * a.oC;
+          rbase = (((long long)R.n * OH + y0) * OW + x0) * oC;
         } else {
-          const int Hs = a.OH / ob + 1, Ws = a.OW / ob + 1;
+          const int Hs = OH / ob + 1, Ws = OW / ob + 1;
           if (a.row_sy > 0) {
-            rbase = ((((long long)R.n * Hs + (long long)Rl * a.row_sy) * Ws + (long long)U * a.row_sx) * ob * ob) * a.oC;
+            rbase = ((((long long)R.n * Hs + (long long)Rl * a.row_sy) * Ws + (long long)U * a.row_sx) * ob * ob) * oC;
           } else if (a.row_sy < 0) {
             rbase = 0;                       // blocks not aligned to the space-to-depth grid: full address per segment
           } else {
             const int yy = y0 + (ob >> 1), xx = x0 + (ob >> 1);
             const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
-            rbase = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * a.oC;
+            rbase = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * oC;
           }
         }
-        const bool edge = (y0 + a.ry > a.OH) || (x0 + a.rx > a.OW);
-        // residual input of this row (same NHWC position as the output): fetched two chunks ahead of use
-        const uint4* sp = nullptr;
-        uint4 sk0[2], sk1[2], sk2[2];
-        if (SKIP) {
-          sp = a.skip + (rbase >> 3) + cpart * 2;
-          if (valid) {
-            sk0[0] = __ldg(sp); sk0[1] = __ldg(sp + 1);
-            if (N > 16 * NEW) { sk1[0] = __ldg(sp + 2 * NEW); sk1[1] = __ldg(sp + 2 * NEW + 1); }
-          }
+        const bool edge = (y0 + ry > OH) || (x0 + rx > OW);
+        // residual input of this row (same NHWC position as the output): all of this thread's chunks are fetched
+        // up front, before the accumulator is ready, so the loads hide behind the MMAs (N <= 128: <= 4 chunks)
+        uint4 sk[4][2];
+        if (SKIP && valid) {
+          const uint4* sp = a.skip + (rbase >> 3) + cpart * 2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (cpart * 16 + k * 16 * NEW < N) ld_global_nc_v8(sp + k * 2 * NEW, sk[k][0], sk[k][1]);
         }
         if (!waited) {
           W_TWAIT(0, mbar_wait(&tfull[as], apar));
           tc_fence_after();
           waited = true;
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(a.T_r * N) + (uint32_t)(mt * N);
-#pragma unroll 1
-        for (int c0 = cpart * 16; c0 < N; c0 += 16 * NEW) {
-          if (SKIP && valid && c0 + 32 * NEW < N) {
-            sk2[0] = __ldg(sp + (c0 >> 3) + 4 * NEW - cpart * 2);
-            sk2[1] = __ldg(sp + (c0 >> 3) + 4 * NEW - cpart * 2 + 1);
-          }
-          uint32_t v[16];
-          if (a.dbg & 1) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(T_r * N) + (uint32_t)(mt * N);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = 0u;
-          } else {
-            tmem_ld16(taddr + (uint32_t)c0, v);
-            tmem_ld_wait();
-          }
-          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
-          if (OUTF32 && a.seg_shift < 2) {
+        for (int k = 0; k < 4; ++k) {             // N <= 128: at most 4 chunks per epilogue warp
+          const int c0 = cpart * 16 + k * 16 * NEW;
+          if (c0 >= N) break;
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (OUTF32 && seg_shift < 2) {
             // fp32 plane, segments of 1 or 2 pixels (wide-input layers packed with G < 4): scalar stores
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const int n0 = c0 + e;
-              const int sg = n0 >> a.seg_shift, ch = n0 & seg_mask;
-              if (ch >= a.seg_valid || sg >= P.nseg) continue;
+              const int sg = n0 >> seg_shift, ch = n0 & seg_mask;
+              if (ch >= seg_valid || sg >= P.nseg) continue;
               const int seg = P.seg_begin + sg;
-              if (!valid || (a.dbg & 2)) continue;
-              if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
+              if (!valid) continue;
+              if (edge && (y0 + a.seg_oy[seg] >= OH || x0 + a.seg_ox[seg] >= OW)) continue;
               reinterpret_cast<float*>(a.out)[rbase + a.seg_delta[seg] + ch] =
-                  w_act<ACT>(__uint_as_float(v[e]) + s_shift[n0], a.act, a.act_param);
+                  w_act<ACT>(__uint_as_float(v[e]) + s_shift[n0], act, act_param);
             }
           } else if (OUTF32) {
             // fp32 output (single channel plane): segments of >= 4 columns, one float4 per quad
+            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int n0 = c0 + h * 4;
-              const int seg = P.seg_begin + (n0 >> a.seg_shift), ch = n0 & seg_mask;
-              if (ch >= a.seg_valid || (n0 >> a.seg_shift) >= P.nseg) continue;   // warp-uniform
-              if (!valid || (a.dbg & 2)) continue;
-              if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
+              const int seg = P.seg_begin + (n0 >> seg_shift), ch = n0 & seg_mask;
+              if (ch >= seg_valid || (n0 >> seg_shift) >= P.nseg) continue;   // warp-uniform
+              if (!valid) continue;
+              if (edge && (y0 + a.seg_oy[seg] >= OH || x0 + a.seg_ox[seg] >= OW)) continue;
               float* o = reinterpret_cast<float*>(a.out) + (rbase + a.seg_delta[seg] + ch);
               const float4 s4 = sh4[h];
               float4 r;
-              r.x = w_act<ACT>(__uint_as_float(v[h * 4 + 0]) + s4.x, a.act, a.act_param);
-              r.y = w_act<ACT>(__uint_as_float(v[h * 4 + 1]) + s4.y, a.act, a.act_param);
-              r.z = w_act<ACT>(__uint_as_float(v[h * 4 + 2]) + s4.z, a.act, a.act_param);
-              r.w = w_act<ACT>(__uint_as_float(v[h * 4 + 3]) + s4.w, a.act, a.act_param);
-              if (a.seg_valid - ch >= 4) {
+              r.x = w_act<ACT>(__uint_as_float(v[h * 4 + 0]) + s4.x, act, act_param);
+              r.y = w_act<ACT>(__uint_as_float(v[h * 4 + 1]) + s4.y, act, act_param);
+              r.z = w_act<ACT>(__uint_as_float(v[h * 4 + 2]) + s4.z, act, act_param);
+              r.w = w_act<ACT>(__uint_as_float(v[h * 4 + 3]) + s4.w, act, act_param);
+              if (seg_valid - ch >= 4) {
                 *reinterpret_cast<float4*>(o) = r;
               } else {
-                if (ch + 0 < a.seg_valid) o[0] = r.x;
-                if (ch + 1 < a.seg_valid) o[1] = r.y;
-                if (ch + 2 < a.seg_valid) o[2] = r.z;
+                if (ch + 0 < seg_valid) o[0] = r.x;
+                if (ch + 1 < seg_valid) o[1] = r.y;
+                if (ch + 2 < seg_valid) o[2] = r.z;
               }
             }
           } else {
+            const ulonglong2* sh2 = reinterpret_cast<const ulonglong2*>(s_shift + c0);   // 4 fp32 = 2 pairs each
             uint4 o[2];
             long long offs[2];
             bool ok[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int n0 = c0 + h * 8;
-              const int seg = P.seg_begin + (n0 >> a.seg_shift), ch = n0 & seg_mask;
+              const int seg = P.seg_begin + (n0 >> seg_shift), ch = n0 & seg_mask;
               ok[h] = false;
-              if (ch >= a.seg_valid || (n0 >> a.seg_shift) >= P.nseg) continue;   // warp-uniform
-              if (!valid || (a.dbg & 2)) continue;
-              if (edge && (y0 + a.seg_oy[seg] >= a.OH || x0 + a.seg_ox[seg] >= a.OW)) continue;
-              const float4 sa = sh4[h * 2], sb = sh4[h * 2 + 1];
-              float xv[8];
-              xv[0] = __uint_as_float(v[h * 8 + 0]) + sa.x; xv[1] = __uint_as_float(v[h * 8 + 1]) + sa.y;
-              xv[2] = __uint_as_float(v[h * 8 + 2]) + sa.z; xv[3] = __uint_as_float(v[h * 8 + 3]) + sa.w;
-              xv[4] = __uint_as_float(v[h * 8 + 4]) + sb.x; xv[5] = __uint_as_float(v[h * 8 + 5]) + sb.y;
-              xv[6] = __uint_as_float(v[h * 8 + 6]) + sb.z; xv[7] = __uint_as_float(v[h * 8 + 7]) + sb.w;
+              if (ch >= seg_valid || (n0 >> seg_shift) >= P.nseg) continue;   // warp-uniform
+              if (!valid) continue;
+              if (edge && (y0 + a.seg_oy[seg] >= OH || x0 + a.seg_ox[seg] >= OW)) continue;
+              const ulonglong2 sa = sh2[h * 2], sb = sh2[h * 2 + 1];
+              unsigned long long x2[4];
+              x2[0] = w_add2(w_pack_b64(v[h * 8 + 0], v[h * 8 + 1]), sa.x);
+              x2[1] = w_add2(w_pack_b64(v[h * 8 + 2], v[h * 8 + 3]), sa.y);
+              x2[2] = w_add2(w_pack_b64(v[h * 8 + 4], v[h * 8 + 5]), sb.x);
+              x2[3] = w_add2(w_pack_b64(v[h * 8 + 6], v[h * 8 + 7]), sb.y);
               if (SKIP) {
-                const uint4 s4 = sk0[h];
-                const float2 s0 = w_unpack16(s4.x, a.fmt), s1 = w_unpack16(s4.y, a.fmt), s2 = w_unpack16(s4.z, a.fmt),
-                             s3 = w_unpack16(s4.w, a.fmt);
-                xv[0] += s0.x; xv[1] += s0.y; xv[2] += s1.x; xv[3] += s1.y;
-                xv[4] += s2.x; xv[5] += s2.y; xv[6] += s3.x; xv[7] += s3.y;
+                const uint4 s4 = sk[k][h];
+                x2[0] = w_add2(x2[0], w_unpack16_b64<FMT>(s4.x));
+                x2[1] = w_add2(x2[1], w_unpack16_b64<FMT>(s4.y));
+                x2[2] = w_add2(x2[2], w_unpack16_b64<FMT>(s4.z));
+                x2[3] = w_add2(x2[3], w_unpack16_b64<FMT>(s4.w));
               }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) xv[e] = w_act<ACT>(xv[e], a.act, a.act_param);
-              o[h].x = w_pack16<ACT>(xv[0], xv[1], a.fmt); o[h].y = w_pack16<ACT>(xv[2], xv[3], a.fmt);
-              o[h].z = w_pack16<ACT>(xv[4], xv[5], a.fmt); o[h].w = w_pack16<ACT>(xv[6], xv[7], a.fmt);
+              o[h].x = w_finish_pair<ACT, FMT>(x2[0], act, act_param);
+              o[h].y = w_finish_pair<ACT, FMT>(x2[1], act, act_param);
+              o[h].z = w_finish_pair<ACT, FMT>(x2[2], act, act_param);
+              o[h].w = w_finish_pair<ACT, FMT>(x2[3], act, act_param);
               long long off = rbase + a.seg_delta[seg] + ch;
               if (a.row_sy < 0) {
-                const int Hs = a.OH / ob + 1, Ws = a.OW / ob + 1;
+                const int Hs = OH / ob + 1, Ws = OW / ob + 1;
                 const int yy = y0 + a.seg_oy[seg] + (ob >> 1), xx = x0 + a.seg_ox[seg] + (ob >> 1);
                 const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
-                off = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * a.oC + ch;
+                off = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * oC + ch;
               }
               offs[h] = off;
               ok[h] = true;
             }
-            uint16_t* ob16 = reinterpret_cast<uint16_t*>(a.out);
-            if (a.seg_shift >= 4 && ok[0] && ok[1]) {
+            if (seg_shift >= 4 && ok[0] && ok[1]) {
               st_global_v8(ob16 + offs[0], o[0], o[1]);              // both halves in one segment: 32 contiguous bytes
             } else {
               if (ok[0]) *reinterpret_cast<uint4*>(ob16 + offs[0]) = o[0];
               if (ok[1]) *reinterpret_cast<uint4*>(ob16 + offs[1]) = o[1];
             }
-          }
-          if (SKIP) {
-            sk0[0] = sk1[0]; sk0[1] = sk1[1];
-            sk1[0] = sk2[0]; sk1[1] = sk2[1];
           }
         }
       }
@@ -576,7 +589,7 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
     UB = 128; nkb = unit_bytes / 128;
     BP_REQUIRE(unit_bytes % 128 == 0, BP_E_UNSUPPORTED, "window GEMM: unit of %d bytes", unit_bytes);
   }
-  BP_REQUIRE(sp.N >= 16 && sp.N <= 256 && sp.N % 16 == 0, BP_E_UNSUPPORTED, "window GEMM: N=%d", sp.N);
+  BP_REQUIRE(sp.N >= 16 && sp.N <= 128 && sp.N % 16 == 0, BP_E_UNSUPPORTED, "window GEMM: N=%d", sp.N);
   BP_REQUIRE((sp.seg_len & (sp.seg_len - 1)) == 0 && sp.seg_len >= 1, BP_E_UNSUPPORTED, "segment length %d", sp.seg_len);
   const int kpu = UB / 32;
 
@@ -794,13 +807,18 @@ void wconv_free(WLayer* w) {
 
 typedef void (*WKernel)(const CUtensorMap, const WArgs);
 
-// instantiated variants: ReLU (+ residual), PReLU (16-bit / fp32 plane), generic activation switch
-static WKernel pick_kernel(int act, bool skip, bool f32) {
-  if (act == BP_ACT_RELU && !f32) return skip ? wconv_kernel<BP_ACT_RELU, true, false> : wconv_kernel<BP_ACT_RELU, false, false>;
+// instantiated variants: ReLU (+ residual), PReLU (16-bit / fp32 plane), generic activation switch; x operand format
+template <int FMT>
+static WKernel pick_kernel_fmt(int act, bool skip, bool f32) {
+  if (act == BP_ACT_RELU && !f32)
+    return skip ? wconv_kernel<BP_ACT_RELU, true, false, FMT> : wconv_kernel<BP_ACT_RELU, false, false, FMT>;
   if ((act == BP_ACT_PRELU || act == BP_ACT_LEAKY) && !skip)
-    return f32 ? wconv_kernel<BP_ACT_PRELU, false, true> : wconv_kernel<BP_ACT_PRELU, false, false>;
-  if (skip) return f32 ? nullptr : wconv_kernel<-1, true, false>;
-  return f32 ? wconv_kernel<-1, false, true> : wconv_kernel<-1, false, false>;
+    return f32 ? wconv_kernel<BP_ACT_PRELU, false, true, FMT> : wconv_kernel<BP_ACT_PRELU, false, false, FMT>;
+  if (skip) return f32 ? nullptr : wconv_kernel<-1, true, false, FMT>;
+  return f32 ? wconv_kernel<-1, false, true, FMT> : wconv_kernel<-1, false, false, FMT>;
+}
+static WKernel pick_kernel(int act, bool skip, bool f32, int fmt) {
+  return fmt == 0 ? pick_kernel_fmt<0>(act, skip, f32) : pick_kernel_fmt<1>(act, skip, f32);
 }
 
 static int g_w_sms = 0;
@@ -843,7 +861,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
                                      "window GEMM: segmented output into a space-to-depth layout");
   }
   const int grid = std::min(a.total_regions, g_w_sms);
-  WKernel k = pick_kernel(wl->act, skip != nullptr, out.f32);
+  WKernel k = pick_kernel(wl->act, skip != nullptr, out.f32, a.fmt);
   BP_REQUIRE(k != nullptr, BP_E_UNSUPPORTED, "window GEMM: residual add with fp32 output");
   static const int dbg = getenv("BP_V2_DBG") ? atoi(getenv("BP_V2_DBG")) : 0;
   a.dbg = dbg;
