@@ -372,6 +372,26 @@ static int v2_new_act(bp_net* net, ActDesc d, int* idx) {
 
 struct V2Ref { int stack, index; Layer* l; bool w; int need_b; };
 
+// device time of one launch of a built layer over a full chunk (median of three after a warm-up launch)
+static int v2_time_layer(const WLayer* w, const ActDesc& out, const void* skip, int nb, float* ms) {
+  cudaEvent_t e[4];
+  for (auto& x : e) BP_CUDA_TRY(cudaEventCreate(&x));
+  int rc = wconv_launch(w, out, skip, nb, 0);
+  for (int i = 0; i < 4 && rc == BP_OK; ++i) {
+    if (i) rc = wconv_launch(w, out, skip, nb, 0);
+    if (rc == BP_OK && cudaEventRecord(e[i], 0) != cudaSuccess) rc = BP_E_CUDA;
+  }
+  if (rc == BP_OK && cudaStreamSynchronize(0) != cudaSuccess) rc = BP_E_CUDA;
+  float t[3] = {0.f, 0.f, 0.f};
+  for (int i = 0; i < 3 && rc == BP_OK; ++i)
+    if (cudaEventElapsedTime(&t[i], e[i], e[i + 1]) != cudaSuccess) rc = BP_E_CUDA;
+  for (auto& x : e) cudaEventDestroy(x);
+  if (rc != BP_OK) { cudaGetLastError(); return rc; }
+  std::sort(t, t + 3);
+  *ms = t[1];
+  return BP_OK;
+}
+
 // lowers one layer sequence starting from act `cur`; the last layer of a `caller_out` sequence writes the
 // caller's fp32 tiles (tail stencil or fp32 kernel, inverse transform fused)
 static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vector<V2Op>& ops, bool caller_out,
@@ -419,17 +439,33 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       std::vector<WSpec> cands;
       int rc = v2_candidates(*r.l, fmt, Cp, &cands);
       if (rc != BP_OK) return rc;
-      rc = BP_E_UNSUPPORTED;
-      for (const WSpec& sp : cands) {
-        rc = wconv_build(sp, P.acts[cur], net->chunk, &op.w);
-        if (rc != BP_E_UNSUPPORTED) break;
-      }
-      if (rc != BP_OK) return rc;
       op.kind = V2_WCONV; op.in = cur;
       r.l->v2 = true;
       if (d.res == BP_RES_CLOSE) { op.skip = skip; skip = -1; }
       rc = v2_new_act(net, o, &op.out);
       if (rc != BP_OK) return rc;
+      // several formulations of one layer (pixel packing of the narrow stride-1 convolutions): the issue-cycle
+      // model orders them, the device decides -- each one that fits is timed on a full chunk and the fastest kept
+      const int max_tune = getenv("BP_V2_NOTUNE") ? 1 : 8;
+      float best_ms = 0.f;
+      int built = 0;
+      rc = BP_E_UNSUPPORTED;
+      for (const WSpec& sp : cands) {
+        if (built >= max_tune) break;
+        WLayer* w = nullptr;
+        int rb = wconv_build(sp, P.acts[cur], net->chunk, &w);
+        if (rb == BP_E_UNSUPPORTED) continue;
+        if (rb != BP_OK) { rc = rb; break; }
+        ++built;
+        rc = BP_OK;
+        if (cands.size() == 1 || max_tune == 1) { op.w = w; break; }
+        float ms = 0.f;
+        rb = v2_time_layer(w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, net->chunk, &ms);
+        if (rb != BP_OK) { wconv_free(w); rc = rb; break; }
+        if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; }
+        else wconv_free(w);
+      }
+      if (rc != BP_OK) { if (op.w) wconv_free(op.w); op.w = nullptr; return rc; }
       ops.push_back(op);
       cur = op.out;
       if (last && wide_tail) {
