@@ -373,8 +373,10 @@ static int v2_new_act(bp_net* net, ActDesc d, int* idx) {
 struct V2Ref { int stack, index; Layer* l; bool w; int need_b; };
 
 // device time of one launch of a built layer over a full chunk (median of three after a warm-up launch)
+static int g_tune_launches = 0;
 static int v2_time_layer(const WLayer* w, const ActDesc& out, const void* skip, int nb, float* ms) {
   cudaEvent_t e[4];
+  g_tune_launches += 4;
   for (auto& x : e) BP_CUDA_TRY(cudaEventCreate(&x));
   int rc = wconv_launch(w, out, skip, nb, 0);
   for (int i = 0; i < 4 && rc == BP_OK; ++i) {
@@ -466,6 +468,9 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
         else wconv_free(w);
       }
       if (rc != BP_OK) { if (op.w) wconv_free(op.w); op.w = nullptr; return rc; }
+      if (built > 1 && getenv("BP_V2_TUNE_LOG"))
+        fprintf(stderr, "[tune] %d.%d conv %d->%d k%d: %d formulations timed, best %.3f ms (tune launches so far %d)\n",
+                r.stack, r.index, d.cin, d.cout, d.kernel, built, best_ms, g_tune_launches);
       ops.push_back(op);
       cur = op.out;
       if (last && wide_tail) {

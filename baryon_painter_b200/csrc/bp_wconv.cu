@@ -70,6 +70,9 @@ struct WArgs {
   const uint4* skip;
   int OH, OW, oC, ob;
   int row_sy, row_sx;          // ob > 1: block strides of the row base (ry / ob, rx / ob), 0 = general (ry = rx = 1)
+  int ob_shift;                // log2(ob)
+  uint32_t pw_magic;           // floor(2^32 / PW) + 1: flat position / PW by one multiply
+  int msplit;                  // epilogue warps of a lane quarter split the region by M-tile (else by column chunk)
   int seg_oy[W_MAX_SEGS], seg_ox[W_MAX_SEGS];
   long long seg_delta[W_MAX_SEGS];
   float act_param;
@@ -363,49 +366,58 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     const int act = a.act;
     const float act_param = a.act_param;
     uint16_t* const ob16 = reinterpret_cast<uint16_t*>(a.out);
+    // the NEW warps of a lane quarter share a region either by M-tile (narrow accumulators: the per-row address
+    // arithmetic is then done once per row, not once per warp) or by 16-column chunk
+    const bool msplit = a.msplit != 0;
+    const int mt0 = msplit ? cpart : 0, mstep = msplit ? NEW : 1;
+    const int cbase = msplit ? 0 : cpart * 16, cstep = msplit ? 16 : 16 * NEW;
+    const int lin = a.mode == W_LINE;
+    const int PW = a.PW, Wt = a.Wt, OWl = a.OWl, OHl = a.OHl, row_sy = a.row_sy, row_sx = a.row_sx;
+    const uint32_t pw_magic = a.pw_magic;
+    const int obs = a.ob_shift, obm = ob - 1, obh = ob >> 1;
+    const int Hs = (OH >> obs) + 1, Ws = (OW >> obs) + 1;
+    const long long samp = ob == 1 ? (long long)OH * OW * oC : ((long long)Hs * Ws << (2 * obs)) * oC;
     uint32_t as = 0, apar = 0;
     for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x) {
       const WRegion R = w_decode(a, reg);
       const WPhase P = a.phase[R.pi];
+      const long long nbase = (long long)R.n * samp;
+      const int ustrip = R.strip * Wt;
       bool waited = false;
-      for (int mt = 0; mt < T_r; ++mt) {
+      for (int mt = mt0; mt < T_r; mt += mstep) {
         int Rl, c;
-        if (a.mode == W_LINE) {
+        if (lin) {
           Rl = R.l0 + mt;
           c = m;
         } else {
-          const int f = R.rr * T_r * 128 + mt * 128 + m;
-          Rl = f / a.PW;
-          c = f - Rl * a.PW;
+          const uint32_t f = (uint32_t)((R.rr * T_r + mt) * 128 + m);
+          Rl = (int)__umulhi(f, pw_magic);            // f / PW (exact: f * PW < 2^32, checked on the host)
+          c = (int)f - Rl * PW;
         }
-        const int U = R.strip * a.Wt + c;
-        const bool valid = c < a.Wt && U < a.OWl && Rl < a.OHl;
+        const int U = ustrip + c;
+        const bool valid = c < Wt && U < OWl && Rl < OHl;
         // element offset of this row's block and whether any of its pixels can fall outside the image
         const int y0 = Rl * ry, x0 = U * rx;
         long long rbase;
         if (ob == 1) {
-          rbase = (((long long)R.n * OH + y0) * OW + x0) * oC;
+          rbase = nbase + (long long)((y0 * OW + x0) * oC);
+        } else if (row_sy > 0) {
+          rbase = nbase + (long long)(((Rl * row_sy * Ws + U * row_sx) << (2 * obs)) * oC);
+        } else if (row_sy < 0) {
+          rbase = 0;                         // blocks not aligned to the space-to-depth grid: full address per segment
         } else {
-          const int Hs = OH / ob + 1, Ws = OW / ob + 1;
-          if (a.row_sy > 0) {
-            rbase = ((((long long)R.n * Hs + (long long)Rl * a.row_sy) * Ws + (long long)U * a.row_sx) * ob * ob) * oC;
-          } else if (a.row_sy < 0) {
-            rbase = 0;                       // blocks not aligned to the space-to-depth grid: full address per segment
-          } else {
-            const int yy = y0 + (ob >> 1), xx = x0 + (ob >> 1);
-            const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
-            rbase = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * oC;
-          }
+          const int yy = y0 + obh, xx = x0 + obh;
+          rbase = nbase + (long long)((((((yy >> obs) * Ws + (xx >> obs)) << obs) + (yy & obm)) << obs) + (xx & obm)) * oC;
         }
         const bool edge = (y0 + ry > OH) || (x0 + rx > OW);
         // residual input of this row (same NHWC position as the output): all of this thread's chunks are fetched
         // up front, before the accumulator is ready, so the loads hide behind the MMAs (N <= 128: <= 4 chunks)
         uint4 sk[4][2];
         if (SKIP && valid) {
-          const uint4* sp = a.skip + (rbase >> 3) + cpart * 2;
+          const uint4* sp = a.skip + ((rbase + cbase) >> 3);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (cpart * 16 + k * 16 * NEW < N) ld_global_nc_v8(sp + k * 2 * NEW, sk[k][0], sk[k][1]);
+            if (cbase + k * cstep < N) ld_global_nc_v8(sp + k * (cstep >> 3), sk[k][0], sk[k][1]);
         }
         if (!waited) {
           W_TWAIT(0, mbar_wait(&tfull[as], apar));
@@ -414,8 +426,8 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(T_r * N) + (uint32_t)(mt * N);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {             // N <= 128: at most 4 chunks per epilogue warp
-          const int c0 = cpart * 16 + k * 16 * NEW;
+        for (int k = 0; k < 4; ++k) {             // at most 4 chunks per epilogue warp (N <= 128, or <= 64 split by M-tile)
+          const int c0 = cbase + k * cstep;
           if (c0 >= N) break;
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
@@ -489,11 +501,9 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               o[h].z = w_finish_pair<ACT, FMT>(x2[2], act, act_param);
               o[h].w = w_finish_pair<ACT, FMT>(x2[3], act, act_param);
               long long off = rbase + a.seg_delta[seg] + ch;
-              if (a.row_sy < 0) {
-                const int Hs = OH / ob + 1, Ws = OW / ob + 1;
-                const int yy = y0 + a.seg_oy[seg] + (ob >> 1), xx = x0 + a.seg_ox[seg] + (ob >> 1);
-                const int by = yy / ob, sy = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
-                off = (((((long long)R.n * Hs + by) * Ws + bx) * ob + sy) * ob + sx) * oC + ch;
+              if (row_sy < 0) {
+                const int yy = y0 + a.seg_oy[seg] + obh, xx = x0 + a.seg_ox[seg] + obh;
+                off = nbase + (long long)((((((yy >> obs) * Ws + (xx >> obs)) << obs) + (yy & obm)) << obs) + (xx & obm)) * oC + ch;
               }
               offs[h] = off;
               ok[h] = true;
@@ -507,6 +517,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
           }
         }
       }
+      if (!waited) mbar_wait(&tfull[as], apar);   // a warp without an M-tile of its own still follows the phases
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       if (++as == 2u) { as = 0; apar ^= 1u; }
@@ -834,6 +845,13 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   a.out = out.ptr;
   a.skip = static_cast<const uint4*>(skip);
   a.OH = out.H; a.OW = out.W; a.ob = out.b;
+  BP_REQUIRE(out.b == 1 || out.b == 2 || out.b == 4 || out.b == 8, BP_E_INVALID, "window conv: output block %d", out.b);
+  a.ob_shift = out.b == 1 ? 0 : out.b == 2 ? 1 : out.b == 4 ? 2 : 3;
+  a.pw_magic = (uint32_t)((1ull << 32) / (unsigned)a.PW) + 1u;
+  BP_REQUIRE((unsigned long long)(a.regs_per_strip + 1) * a.T_r * 128ull * (unsigned)a.PW < (1ull << 32) &&
+                 out.bytes_per_sample() < (1ull << 31),
+             BP_E_UNSUPPORTED, "window conv: tile too large for 32-bit row arithmetic");
+  a.msplit = (a.N <= 64 && a.T_r >= 2 && !getenv("BP_V2_NOMSPLIT")) ? 1 : 0;
   a.oC = out.f32 ? 1 : out.Cp;
   BP_REQUIRE(!out.f32 || out.C == 1, BP_E_UNSUPPORTED, "window GEMM: fp32 output with %d channels", out.C);
   BP_REQUIRE(!skip || (out.b == 1 && !out.f32 && a.N <= 128 && a.ry == 1 && a.rx == 1), BP_E_UNSUPPORTED,
