@@ -32,8 +32,10 @@ namespace bp {
 
 using namespace tc;
 
-constexpr int W_EPI_WARPS = 8;            // epilogue warps (two per TMEM lane quarter, interleaved over column chunks)
-constexpr int W_THREADS = 128 + 32 * W_EPI_WARPS;
+// epilogue warps: four per TMEM lane quarter, two for the residual variants (their 32-register prefetch of the
+// skip input does not fit the 96-register budget of a 640-thread CTA, and those layers are tensor-bound anyway)
+constexpr int w_epi_warps(bool skip) { return skip ? 8 : 16; }
+constexpr int w_threads(bool skip) { return 128 + 32 * w_epi_warps(skip); }
 constexpr int W_PSTAGES = 2;
 constexpr int W_BSTAGES = 4;              // barrier slots; a layer uses a.nbst <= 4 weight stages
 constexpr int W_MAX_SEGS = 32;
@@ -72,7 +74,7 @@ struct WArgs {
   int row_sy, row_sx;          // ob > 1: block strides of the row base (ry / ob, rx / ob), 0 = general (ry = rx = 1)
   int ob_shift;                // log2(ob)
   uint32_t pw_magic;           // floor(2^32 / PW) + 1: flat position / PW by one multiply
-  int msplit;                  // epilogue warps of a lane quarter split the region by M-tile (else by column chunk)
+  int msplit;                  // M-tile parts the epilogue warps of one lane quarter split a region into
   int seg_oy[W_MAX_SEGS], seg_ox[W_MAX_SEGS];
   long long seg_delta[W_MAX_SEGS];
   float act_param;
@@ -260,7 +262,7 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
 }
 
 template <int ACT, bool SKIP, bool OUTF32, int FMT>
-__global__ void __launch_bounds__(W_THREADS, 1)
+__global__ void __launch_bounds__(w_threads(SKIP), 1)
 wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sP = smem;
@@ -280,14 +282,14 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
   long long tacc[3] = {0, 0, 0};
   const long long t_start = a.timing ? clock64() : 0;
 
-  for (int i = tid; i < N; i += W_THREADS) s_shift[i] = a.shift[i];
+  for (int i = tid; i < N; i += w_threads(SKIP)) s_shift[i] = a.shift[i];
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full_p[s], 1);
       mbar_init(&empty_p[s], 1);
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 32 * W_EPI_WARPS);
+      mbar_init(&tempty[s], 32 * w_epi_warps(SKIP));
     }
     for (int s = 0; s < W_BSTAGES; ++s) {
       mbar_init(&full_b[s], 1);
@@ -354,10 +356,11 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // warp = 4 + e: TMEM lane quarter e % 4 (a warp may only touch lanes 32*(warp % 4) ..), 16-column chunks
-    // e / 4, e / 4 + W_EPI_WARPS / 4, ...  One thread = one M row; a chunk's two 8-column halves are 16-byte
-    // stores (one 32-byte store when both lie in one segment) to row_base + seg_delta[segment] (+ channel).
-    constexpr int NEW = W_EPI_WARPS / 4;
+    // warp = 4 + e: TMEM lane quarter e % 4 (a warp may only touch lanes 32*(warp % 4) ..); the NEW warps of a
+    // quarter take every msplit-th M-tile and every (NEW / msplit)-th 16-column chunk.  One thread = one M row; a
+    // chunk's two 8-column halves are 16-byte stores (one 32-byte store when both lie in one segment) to
+    // row_base + seg_delta[segment] (+ channel).
+    constexpr int NEW = w_epi_warps(SKIP) / 4;
     const int q = warp & 3;
     const int cpart = (warp - 4) >> 2;
     const int m = q * 32 + lane;
@@ -368,9 +371,9 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     uint16_t* const ob16 = reinterpret_cast<uint16_t*>(a.out);
     // the NEW warps of a lane quarter share a region either by M-tile (narrow accumulators: the per-row address
     // arithmetic is then done once per row, not once per warp) or by 16-column chunk
-    const bool msplit = a.msplit != 0;
-    const int mt0 = msplit ? cpart : 0, mstep = msplit ? NEW : 1;
-    const int cbase = msplit ? 0 : cpart * 16, cstep = msplit ? 16 : 16 * NEW;
+    const int mstep = a.msplit, cparts = NEW / mstep;          // M-tile parts x column parts = NEW
+    const int mt0 = cpart / cparts;
+    const int cbase = (cpart % cparts) * 16, cstep = 16 * cparts;
     const int lin = a.mode == W_LINE;
     const int PW = a.PW, Wt = a.Wt, OWl = a.OWl, OHl = a.OHl, row_sy = a.row_sy, row_sx = a.row_sx;
     const uint32_t pw_magic = a.pw_magic;
@@ -851,7 +854,16 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   BP_REQUIRE((unsigned long long)(a.regs_per_strip + 1) * a.T_r * 128ull * (unsigned)a.PW < (1ull << 32) &&
                  out.bytes_per_sample() < (1ull << 31),
              BP_E_UNSUPPORTED, "window conv: tile too large for 32-bit row arithmetic");
-  a.msplit = (a.N <= 64 && a.T_r >= 2 && !getenv("BP_V2_NOMSPLIT")) ? 1 : 0;
+  {
+    // split of a region over the epilogue warps of one lane quarter: as many M-tile parts as T_r allows while a
+    // warp keeps at most four 16-column chunks of an M-tile
+    const int new_ = w_epi_warps(skip != nullptr) / 4;
+    int ms = 1;
+    while (ms * 2 <= new_ && ms * 2 <= a.T_r) ms *= 2;
+    while (ms > 1 && ((a.N + 15) / 16 + new_ / ms - 1) / (new_ / ms) > 4) ms /= 2;
+    BP_REQUIRE(((a.N + 15) / 16 + new_ / ms - 1) / (new_ / ms) <= 4, BP_E_UNSUPPORTED, "window conv: N = %d too wide", a.N);
+    a.msplit = ms;
+  }
   a.oC = out.f32 ? 1 : out.Cp;
   BP_REQUIRE(!out.f32 || out.C == 1, BP_E_UNSUPPORTED, "window GEMM: fp32 output with %d channels", out.C);
   BP_REQUIRE(!skip || (out.b == 1 && !out.f32 && a.N <= 128 && a.ry == 1 && a.rx == 1), BP_E_UNSUPPORTED,
@@ -891,7 +903,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
     a.timing = d_timing;
   }
   BP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_LIMIT));
-  k<<<grid, W_THREADS, wl->smem, s>>>(wl->tmap, a);
+  k<<<grid, w_threads(skip != nullptr), wl->smem, s>>>(wl->tmap, a);
   launch_counter()++;
   BP_CUDA_TRY(cudaGetLastError());
   if (timing) {
