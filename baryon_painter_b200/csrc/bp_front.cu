@@ -79,55 +79,153 @@ int launch_front_prior(const float* tiles, const ActDesc& out, const float* sigm
 }
 
 // ---- prior input fused with prior_network.0 (k4 s2 p1, 2 -> <= 8 channels, BN + activation) -----------------
-// CTA = 32 x 32 output pixels: the 66 x 66 window of raw densities is transformed once into shared memory,
-// every thread produces 4 output pixels x 8 channels (FFMA, weights in the constant bank) and writes 16 bytes
-// per pixel into the layout the next layer reads.  The constant z plane contributes z * (sum of the in-image
-// taps' weights); only the border outputs see fewer taps.
-__global__ void __launch_bounds__(256) front_prior_conv_kernel(const float* __restrict__ tiles, uint16_t* __restrict__ out,
-                                                               const float* __restrict__ sigma, const float* __restrict__ aux,
-                                                               const FrontConvParams fc, float k_in, float shift_in, int do_t,
-                                                               int H, int W, int ob, int oCp, int fmt) {
-  __shared__ float sy[66][67];
+// CTA = 32 x 32 output pixels: the 66 x 66 window of raw densities is transformed once into shared memory.
+// A thread owns 4 vertically adjacent outputs x 8 channels: its 10 x 4 input window sits in registers as
+// column pairs (64-bit shared loads), the weights come as matching pairs from shared memory and every
+// fma.rn.f32x2 advances one (pixel, channel) accumulator by two taps; the two halves are summed at the end.
+// The constant z plane contributes z * (sum of the in-image taps' weights): a per-channel constant away from
+// the image border.
+__device__ __forceinline__ unsigned long long f_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f_pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+// two fp32 -> one packed 16-bit pair (lo in the low half), saturating to the finite range
+__device__ __forceinline__ uint32_t f_pack16(float lo, float hi, int fmt) {
+  uint32_t r;
+  if (fmt == 0) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f_sum2(unsigned long long v) {
+  return __uint_as_float((uint32_t)v) + __uint_as_float((uint32_t)(v >> 32));
+}
+
+__global__ void __launch_bounds__(256, 2) front_prior_conv_kernel(const float* __restrict__ tiles, uint16_t* __restrict__ out,
+                                                                  const float* __restrict__ sigma, const float* __restrict__ aux,
+                                                                  const FrontConvParams fc, float k_in, float shift_in, int do_t,
+                                                                  int H, int W, int ob, int oCp, int fmt) {
+  __shared__ __align__(16) float sy[66][68];
+  __shared__ __align__(16) unsigned long long sw[4][2][8];     // [r][column pair][co] = {w(r, 2qp), w(r, 2qp + 1)}
+  __shared__ float szs[3][3][8];          // z tap sums by (row class, column class): first / interior / last
   const int n = blockIdx.z;
   const int OH = H >> 1, OW = W >> 1;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
   const float z = aux[n];
   const float* src = tiles + (size_t)n * H * W;
-  for (int t = threadIdx.x; t < 66 * 66; t += blockDim.x) {
-    const int ly = t / 66, lx = t - ly * 66;
-    const int y = 2 * i0 - 1 + ly, x = 2 * j0 - 1 + lx;
-    sy[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? f_transform(__ldg(src + (size_t)y * W + x), sg, ik, shift_in, do_t) : 0.f;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  if (tid < 64) {
+    const int r = tid >> 4, qp = (tid >> 3) & 1, co = tid & 7;
+    sw[r][qp][co] = f_pack2(fc.w[co][0][r * 4 + 2 * qp], fc.w[co][0][r * 4 + 2 * qp + 1]);
+  } else if (tid < 64 + 72) {
+    const int t = tid - 64;
+    (&szs[0][0][0])[t] = (&fc.zsum[0][0][0])[t];
   }
-  __syncthreads();
-  const int lj = threadIdx.x & 31, li0 = (threadIdx.x >> 5) * 4;
-  const int j = j0 + lj;
-  if (j >= OW) return;
-#pragma unroll 1
-  for (int r4 = 0; r4 < 4; ++r4) {
-    const int li = li0 + r4, i = i0 + li;
-    if (i >= OH) break;
-    float acc[8];
+  if ((W & 3) == 0 && 2 * j0 + 64 <= W) {
+    // window = columns 2 j0 - 1 .. 2 j0 + 64: the 64 interior columns come as aligned float4 (16 per row), the two
+    // halo columns as scalars; all of a thread's loads are issued before the first is consumed (two CTAs per SM:
+    // the latency has to be covered inside the thread)
+    constexpr int NV = (66 * 16 + 255) / 256;
+    float4 raw[NV];
 #pragma unroll
-    for (int co = 0; co < 8; ++co) acc[co] = 0.f;
+    for (int k = 0; k < NV; ++k) {
+      const int t = tid + k * 256, ly = t >> 4, q = t & 15;
+      const int y = 2 * i0 - 1 + ly;
+      raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ly < 66 && y >= 0 && y < H) raw[k] = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * W + 2 * j0) + q);
+    }
+    float hv = 0.f;
+    const int hly = tid >> 1, hlx = (tid & 1) * 65;
+    const int hy = 2 * i0 - 1 + hly, hx = 2 * j0 - 1 + hlx;
+    const bool hok = hly < 66 && hy >= 0 && hy < H && hx >= 0 && hx < W;
+    if (hok) hv = __ldg(src + (size_t)hy * W + hx);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const bool rin = !(i == 0 && r == 0) && !(i == OH - 1 && r == 3);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const bool cin_ = !(j == 0 && q == 0) && !(j == OW - 1 && q == 3);
-        const float yv = sy[2 * li + r][2 * lj + q];
-        const float zv = (rin && cin_) ? z : 0.f;
-#pragma unroll
-        for (int co = 0; co < 8; ++co) acc[co] = fmaf(yv, fc.w[co][0][r * 4 + q], fmaf(zv, fc.w[co][1][r * 4 + q], acc[co]));
+    for (int k = 0; k < NV; ++k) {
+      const int t = tid + k * 256, ly = t >> 4, q = t & 15;
+      const int y = 2 * i0 - 1 + ly;
+      if (ly < 66) {
+        const bool ok = y >= 0 && y < H;
+        float* d = &sy[ly][1 + 4 * q];
+        d[0] = ok ? f_transform(raw[k].x, sg, ik, shift_in, do_t) : 0.f;
+        d[1] = ok ? f_transform(raw[k].y, sg, ik, shift_in, do_t) : 0.f;
+        d[2] = ok ? f_transform(raw[k].z, sg, ik, shift_in, do_t) : 0.f;
+        d[3] = ok ? f_transform(raw[k].w, sg, ik, shift_in, do_t) : 0.f;
       }
     }
+    if (hly < 66) sy[hly][hlx] = hok ? f_transform(hv, sg, ik, shift_in, do_t) : 0.f;
+  } else {
+    for (int t = tid; t < 66 * 66; t += 256) {
+      const int ly = t / 66, lx = t - ly * 66;
+      const int y = 2 * i0 - 1 + ly, x = 2 * j0 - 1 + lx;
+      sy[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? f_transform(__ldg(src + (size_t)y * W + x), sg, ik, shift_in, do_t) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int lj = lane, li0 = wrp * 4;
+  const int j = j0 + lj;
+  if (j >= OW || i0 + li0 >= OH) return;
+  unsigned long long yv[10][2];
+#pragma unroll
+  for (int rr = 0; rr < 10; ++rr) {
+    yv[rr][0] = *reinterpret_cast<const unsigned long long*>(&sy[2 * li0 + rr][2 * lj]);
+    yv[rr][1] = *reinterpret_cast<const unsigned long long*>(&sy[2 * li0 + rr][2 * lj + 2]);
+  }
+  unsigned long long acc[4][8];
+  {
+    const int cc = j == 0 ? 0 : (j == OW - 1 ? 2 : 1);
+    float zc[8];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) zc[co] = z * szs[1][cc][co];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int i = i0 + li0 + p;
+      if (i == 0 || i == OH - 1) {                        // warp-uniform
+        const int rc = i == 0 ? 0 : 2;
+#pragma unroll
+        for (int co = 0; co < 8; ++co) acc[p][co] = f_pack2(z * szs[rc][cc][co], 0.f);
+      } else {
+#pragma unroll
+        for (int co = 0; co < 8; ++co) acc[p][co] = f_pack2(zc[co], 0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int qp = 0; qp < 2; ++qp) {
+      unsigned long long w2[8];
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(&sw[r][qp][2 * c2]);
+        w2[2 * c2] = t.x; w2[2 * c2 + 1] = t.y;
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int co = 0; co < 8; ++co) acc[p][co] = f_fma2(yv[2 * p + r][qp], w2[co], acc[p][co]);
+    }
+  const bool lin_act = fc.act == BP_ACT_RELU || fc.act == BP_ACT_LEAKY || fc.act == BP_ACT_PRELU || fc.act == BP_ACT_NONE;
+  const float slope = fc.act == BP_ACT_RELU ? 0.f : (fc.act == BP_ACT_NONE ? 1.f : fc.act_param);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = i0 + li0 + p;
+    if (i >= OH) break;
     uint32_t pk[4];
 #pragma unroll
     for (int c2 = 0; c2 < 4; ++c2) {
-      const float a0 = f_act(acc[2 * c2] + fc.shift[2 * c2], fc.act, fc.act_param);
-      const float a1 = f_act(acc[2 * c2 + 1] + fc.shift[2 * c2 + 1], fc.act, fc.act_param);
-      pk[c2] = (uint32_t)f_to16(2 * c2 < fc.cout ? a0 : 0.f, fmt) | ((uint32_t)f_to16(2 * c2 + 1 < fc.cout ? a1 : 0.f, fmt) << 16);
+      float a0 = f_sum2(acc[p][2 * c2]) + fc.shift[2 * c2], a1 = f_sum2(acc[p][2 * c2 + 1]) + fc.shift[2 * c2 + 1];
+      if (lin_act) {                                      // ReLU / LeakyReLU / PReLU: one select
+        a0 = a0 >= 0.f ? a0 : a0 * slope;
+        a1 = a1 >= 0.f ? a1 : a1 * slope;
+      } else {
+        a0 = f_act(a0, fc.act, fc.act_param);
+        a1 = f_act(a1, fc.act, fc.act_param);
+      }
+      pk[c2] = f_pack16(2 * c2 < fc.cout ? a0 : 0.f, 2 * c2 + 1 < fc.cout ? a1 : 0.f, fmt);
     }
     size_t o;
     if (ob == 1) {
@@ -215,10 +313,55 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
     __syncthreads();
   }
   const int L = pz.nl - 1;
+  const bool fast4 = pz.s[L] == 4 && pz.k[L] == 8 && pz.p[L] == 2 && (W & 3) == 0 && ((W >> 2) & ((W >> 2) - 1)) == 0 &&
+                     lvw[L] * 4 == W;
   const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
   const uint32_t z16 = f_to16(aux[n], fmt);
   const int nr = hi[pz.nl] - lo[pz.nl] + 1;
   const float* src = buf[L] - (size_t)lo[L] * lvw[L];
+  if (fast4) {
+    // last level k8 s4 p2, four pixels (one input column period) per thread: the quad reads a 2 x 3 input window
+    // and two weight rows chosen by oy mod 4, with no per-pixel index arithmetic
+    //   ox + e: e = 0, 1 -> columns (2, 3) of in[xq], (6, 7) of in[xq - 1];  e = 2, 3 -> (0, 1) of in[xq + 1], (4, 5) of in[xq]
+    __shared__ __align__(16) float swz[64];
+    if (threadIdx.x < 64) swz[threadIdx.x] = pz.w[L][threadIdx.x];
+    __syncthreads();
+    const int W4 = W >> 2, w4s = 31 - __clz(W4), iw = lvw[L], ih = hi[L] + 1;
+    const float bsc = pz.scale[L], bsh = pz.shift[L], ap = pz.act_param[L];
+    const int actL = pz.act[L];
+    for (int i = threadIdx.x; i < nr * W4; i += blockDim.x) {
+      const int oy = y0 + (i >> w4s), xq = i & (W4 - 1), ox = xq * 4;
+      const size_t p = ((size_t)n * H + oy) * W + ox;
+      const float4 t = __ldg(reinterpret_cast<const float4*>(tiles + p));
+      const int ty = oy + 2, r0 = ty & 3, qh = ty >> 2;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int iy = qh - a;
+        if (iy < 0 || iy >= ih) continue;           // uniform over the row
+        const float* row = src + iy * iw;
+        const float vm = xq > 0 ? row[xq - 1] : 0.f, v0 = row[xq], vp = xq + 1 < iw ? row[xq + 1] : 0.f;
+        const float4 wa = *reinterpret_cast<const float4*>(&swz[(r0 + 4 * a) * 8]);
+        const float4 wb = *reinterpret_cast<const float4*>(&swz[(r0 + 4 * a) * 8 + 4]);
+        acc[0] = fmaf(v0, wa.z, fmaf(vm, wb.z, acc[0]));
+        acc[1] = fmaf(v0, wa.w, fmaf(vm, wb.w, acc[1]));
+        acc[2] = fmaf(vp, wa.x, fmaf(v0, wb.x, acc[2]));
+        acc[3] = fmaf(vp, wa.y, fmaf(v0, wb.y, acc[3]));
+      }
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+      uint32_t lo16[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = fmaf(acc[e], bsc, bsh);
+        v = actL == BP_ACT_RELU ? fmaxf(v, 0.f) : f_act(v, actL, ap);
+        lo16[e] = (uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(f_transform(tv[e], sg, ik, shift_in, do_t), fmt) << 16);
+      }
+      uint4* o = reinterpret_cast<uint4*>(out + p);
+      o[0] = make_uint4(lo16[0], z16, lo16[1], z16);
+      o[1] = make_uint4(lo16[2], z16, lo16[3], z16);
+    }
+    return;
+  }
   if ((W & 3) == 0) {
     // four pixels per thread: one 16-byte tile load, two 16-byte NHWC stores
     const int W4 = W >> 2;
@@ -282,20 +425,40 @@ int launch_front_latent(const float* tiles, const float* latent, const ActDesc& 
 }
 
 // ---- tail: 1 -> 1 channel k x k convolution (fp32) + activation + inverse transform ------------------
+// CTA = 64 x 16 outputs, 4 along x per thread.  The shared tile keeps the image column x0 at a 16-byte aligned
+// offset (4 floats in), so a thread's window is one float4 plus R scalars either side per row.
 template <int K>
 __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            long long out_bs, const TailParams tp,
                                                            const float* __restrict__ post_sigma, int H, int W) {
   constexpr int R = K / 2;
-  constexpr int TX = 64, TY = 16;                 // tile of outputs per CTA; 4 outputs per thread along x
-  __shared__ float sh[TY + 2 * R][TX + 2 * R + 1];
+  constexpr int TX = 64, TY = 16, SW = TX + 8;      // row stride 72 floats: offset 4 + [-R, TX + R)
+  static_assert(R <= 4, "halo must fit the 4-float margins");
+  __shared__ __align__(16) float sh[TY + 2 * R][SW];
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const float* src = in + (size_t)n * H * W;
-  for (int i = threadIdx.x; i < (TY + 2 * R) * (TX + 2 * R); i += blockDim.x) {
-    const int ly = i / (TX + 2 * R), lx = i - ly * (TX + 2 * R);
-    const int y = y0 + ly - R, x = x0 + lx - R;
-    sh[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (size_t)y * W + x) : 0.f;
+  if ((W & 3) == 0 && x0 + TX <= W) {
+    // interior columns as aligned float4 (16 per row), the 2R halo columns as scalars
+    for (int i = threadIdx.x; i < (TY + 2 * R) * (TX / 4); i += 256) {
+      const int ly = i / (TX / 4), q = i - ly * (TX / 4);
+      const int y = y0 + ly - R;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= 0 && y < H) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * W + x0) + q);
+      *reinterpret_cast<float4*>(&sh[ly][4 + 4 * q]) = v;
+    }
+    for (int i = threadIdx.x; i < (TY + 2 * R) * 2 * R; i += 256) {
+      const int ly = i / (R > 0 ? 2 * R : 1), h = i - ly * (2 * R);
+      const int lx = h < R ? h : TX + h;                 // [0, R) left of the block, [TX + R, TX + 2R) right of it
+      const int y = y0 + ly - R, x = x0 + lx - R;
+      sh[ly][4 - R + lx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (size_t)y * W + x) : 0.f;
+    }
+  } else {
+    for (int i = threadIdx.x; i < (TY + 2 * R) * (TX + 2 * R); i += 256) {
+      const int ly = i / (TX + 2 * R), lx = i - ly * (TX + 2 * R);
+      const int y = y0 + ly - R, x = x0 + lx - R;
+      sh[ly][4 - R + lx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (size_t)y * W + x) : 0.f;
+    }
   }
   __syncthreads();
   const int ty = threadIdx.x / 16, tx = (threadIdx.x % 16) * 4;
@@ -303,13 +466,22 @@ __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restri
   if (y >= H) return;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int r = 0; r < K; ++r)
+  for (int r = 0; r < K; ++r) {
+    float v[4 + 2 * R];
+    const float4 c4 = *reinterpret_cast<const float4*>(&sh[ty + r][4 + tx]);
+    v[R] = c4.x; v[R + 1] = c4.y; v[R + 2] = c4.z; v[R + 3] = c4.w;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      v[q] = sh[ty + r][4 + tx - R + q];
+      v[R + 4 + q] = sh[ty + r][4 + tx + 4 + q];
+    }
 #pragma unroll
     for (int q = 0; q < K; ++q) {
       const float w = tp.w[r * K + q];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] = fmaf(sh[ty + r][tx + e + q], w, acc[e]);
+      for (int e = 0; e < 4; ++e) acc[e] = fmaf(v[e + q], w, acc[e]);
     }
+  }
   const float sg = tp.post ? post_sigma[n] : 1.f;
   float o[4];
 #pragma unroll

@@ -34,6 +34,7 @@ struct FrontConvParams {
   float act_param;
   float w[8][2][16];          // [co][ci][r*4 + q], BN scale folded in
   float shift[8];
+  float zsum[3][3][8];        // sum of the z-channel taps inside the image, by (row, column) border class
 };
 
 int launch_front_prior_conv(const float* tiles, const ActDesc& out, const float* sigma, const float* aux,

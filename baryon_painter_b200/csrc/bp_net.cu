@@ -464,6 +464,8 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
         float ms = 0.f;
         rb = v2_time_layer(w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, net->chunk, &ms);
         if (rb != BP_OK) { wconv_free(w); rc = rb; break; }
+        if (getenv("BP_V2_TUNE_LOG"))
+          fprintf(stderr, "[tune]   %d.%d N=%d G=%d Jy=%d mode=%d: %.3f ms\n", r.stack, r.index, sp.N, sp.G, sp.Jy, sp.mode, ms);
         if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; }
         else wconv_free(w);
       }
@@ -607,6 +609,14 @@ static int v2_build(bp_net* net) {
           P.fc.shift[co] = prl[0].host_shift[co];
           for (int ci = 0; ci < 2; ++ci)
             for (int t = 0; t < 16; ++t) P.fc.w[co][ci][t] = prl[0].host_weight[((size_t)co * 2 + ci) * 16 + t] * prl[0].host_scale[co];
+          // z-plane tap sums by border class (first / interior / last row and column): the padded taps drop out
+          for (int rc_ = 0; rc_ < 3; ++rc_)
+            for (int cc = 0; cc < 3; ++cc) {
+              float sz = 0.f;
+              for (int r = (rc_ == 0 ? 1 : 0); r < (rc_ == 2 ? 3 : 4); ++r)
+                for (int q = (cc == 0 ? 1 : 0); q < (cc == 2 ? 3 : 4); ++q) sz += P.fc.w[co][1][r * 4 + q];
+              P.fc.zsum[rc_][cc][co] = sz;
+            }
         }
         ActDesc a; a.C = d0.cout; a.Cp = 8; a.H = net->H / 2; a.W = net->W / 2; a.b = ps[1].need_b;
         rc = v2_new_act(net, a, &P.prior_in);

@@ -9,6 +9,7 @@
 //                                            while s*s*Cout <= 128
 // Reference modules: baryon_painter/models/utils.py:40-77 (conv_block scale 1/2/4), :128-131.
 #include <algorithm>
+#include <functional>
 
 #include "bp_wconv.h"
 
@@ -208,6 +209,44 @@ static int make_spec_packed(const Layer& l, int fmt, int Cp, int G, int Jy, WSpe
   return BP_OK;
 }
 
+// J consecutive M lines of a single-phase formulation folded into one (Toeplitz expansion along y): the tap grid
+// grows by (J - 1) * Jy lines, N by the factor J.  Narrow strided / transposed layers trade a few zero weights
+// for J times the work per A-operand read.
+static bool pack_lines(const WSpec& base, int J, WSpec* out) {
+  if (base.nphase != 1 || base.N * J > 128 || (int)base.segs[0].size() * base.seg_len != base.N) return false;
+  *out = base;
+  out->mode = W_LINE;
+  out->Jy = base.Jy * J;
+  out->ry = base.ry * J;
+  out->OHl = (base.OHl + J - 1) / J;
+  out->N = base.N * J;
+  std::vector<WTap> taps;
+  for (int j = 0; j < J; ++j)
+    for (const WTap& t : base.taps[0]) {
+      const WTap u{t.dl + j * base.Jy, t.du};
+      bool seen = false;
+      for (const WTap& v : taps) seen = seen || (v.dl == u.dl && v.du == u.du);
+      if (!seen) taps.push_back(u);
+    }
+  std::sort(taps.begin(), taps.end(), [](const WTap& a, const WTap& b) { return a.dl != b.dl ? a.dl < b.dl : a.du < b.du; });
+  out->taps[0] = taps;
+  out->segs[0].clear();
+  for (int j = 0; j < J; ++j)
+    for (const WSegOff& sg : base.segs[0]) out->segs[0].push_back({sg.oy + j * base.ry, sg.ox});
+  out->shift.resize(out->N);
+  for (int n = 0; n < out->N; ++n) out->shift[n] = base.shift[n % base.N];
+  const std::vector<WTap> btaps = base.taps[0];
+  const std::function<float(int, int, int, int)> bw = base.weight;
+  const int bN = base.N, bJy = base.Jy;
+  out->weight = [=](int, int t, int elem, int n) -> float {
+    const int j = n / bN, dl = taps[t].dl - j * bJy;
+    for (size_t i = 0; i < btaps.size(); ++i)
+      if (btaps[i].dl == dl && btaps[i].du == taps[t].du) return bw(0, (int)i, elem, n % bN);
+    return 0.f;
+  };
+  return true;
+}
+
 static double mma_cycles(int N) { return std::max(45.5, std::max((4096.0 + 32.0 * N) / 128.0, N / 2.0)); }
 
 // window-GEMM formulations of `l` reading a 16-bit NHWC input with `Cp` stored channels per pixel,
@@ -220,6 +259,12 @@ int v2_candidates(const Layer& l, int fmt, int Cp, std::vector<WSpec>* out) {
     int rc = v2_make_spec(l, fmt, &sp);
     if (rc != BP_OK) return rc;
     out->push_back(sp);
+    // wide single-phase layers: also offer two / four output lines per M row (the build times them)
+    if (sp.nphase == 1 && sp.OWl >= 128 && !getenv("BP_V2_NOLINEPACK"))
+      for (int J : {2, 4}) {
+        WSpec pk;
+        if (pack_lines(sp, J, &pk)) out->push_back(pk);
+      }
     return BP_OK;
   }
   struct Cand { double cost; int G, Jy; };
