@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <new>
 
 #include "bp_common.h"
@@ -374,6 +375,19 @@ struct V2Ref { int stack, index; Layer* l; bool w; int need_b; };
 
 // device time of one launch of a built layer over a full chunk (median of three after a warm-up launch)
 static int g_tune_launches = 0;
+static std::string g_tune_choices;
+static int v2_forced_choice(int stack, int index) {
+  const char* e = getenv("BP_V2_CHOICES");
+  if (!e) return -1;
+  const std::string key = std::to_string(stack) + "." + std::to_string(index) + "=";
+  const std::string sv(e);
+  size_t pos = 0;
+  while ((pos = sv.find(key, pos)) != std::string::npos) {
+    if (pos == 0 || sv[pos - 1] == ',') return atoi(sv.c_str() + pos + key.size());
+    ++pos;
+  }
+  return -1;
+}
 static int v2_time_layer(const WLayer* w, const ActDesc& out, const void* skip, int nb, float* ms) {
   cudaEvent_t e[4];
   g_tune_launches += 4;
@@ -450,9 +464,14 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       // model orders them, the device decides -- each one that fits is timed on a full chunk and the fastest kept
       const int max_tune = getenv("BP_V2_NOTUNE") ? 1 : 8;
       float best_ms = 0.f;
-      int built = 0;
+      int built = 0, ci = -1, best_ci = -1;
+      // BP_V2_CHOICES="stack.index=candidate,..." replays an earlier run's selection without timing (profilers
+      // serialise launches and would perturb it); BP_V2_TUNE_LOG prints the string to replay
+      const int forced = v2_forced_choice(r.stack, r.index);
       rc = BP_E_UNSUPPORTED;
       for (const WSpec& sp : cands) {
+        ++ci;
+        if (forced >= 0 && ci != forced) continue;
         if (built >= max_tune) break;
         WLayer* w = nullptr;
         int rb = wconv_build(sp, P.acts[cur], net->chunk, &w);
@@ -460,19 +479,21 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
         if (rb != BP_OK) { rc = rb; break; }
         ++built;
         rc = BP_OK;
-        if (cands.size() == 1 || max_tune == 1) { op.w = w; break; }
+        if (cands.size() == 1 || max_tune == 1 || forced >= 0) { op.w = w; best_ci = ci; break; }
         float ms = 0.f;
         rb = v2_time_layer(w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, net->chunk, &ms);
         if (rb != BP_OK) { wconv_free(w); rc = rb; break; }
         if (getenv("BP_V2_TUNE_LOG"))
           fprintf(stderr, "[tune]   %d.%d N=%d G=%d Jy=%d mode=%d: %.3f ms\n", r.stack, r.index, sp.N, sp.G, sp.Jy, sp.mode, ms);
-        if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; }
+        if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; best_ci = ci; }
         else wconv_free(w);
       }
       if (rc != BP_OK) { if (op.w) wconv_free(op.w); op.w = nullptr; return rc; }
-      if (built > 1 && getenv("BP_V2_TUNE_LOG"))
-        fprintf(stderr, "[tune] %d.%d conv %d->%d k%d: %d formulations timed, best %.3f ms (tune launches so far %d)\n",
-                r.stack, r.index, d.cin, d.cout, d.kernel, built, best_ms, g_tune_launches);
+      if (built > 1 && getenv("BP_V2_TUNE_LOG")) {
+        g_tune_choices += std::to_string(r.stack) + "." + std::to_string(r.index) + "=" + std::to_string(best_ci) + ",";
+        fprintf(stderr, "[tune] %d.%d conv %d->%d k%d: %d formulations timed, best %.3f ms (tune launches so far %d) BP_V2_CHOICES=%s\n",
+                r.stack, r.index, d.cin, d.cout, d.kernel, built, best_ms, g_tune_launches, g_tune_choices.c_str());
+      }
       ops.push_back(op);
       cur = op.out;
       if (last && wide_tail) {

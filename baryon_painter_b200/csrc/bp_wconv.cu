@@ -34,6 +34,7 @@ using namespace tc;
 
 // epilogue warps: four per TMEM lane quarter, two for the residual variants (their 32-register prefetch of the
 // skip input does not fit the 96-register budget of a 640-thread CTA, and those layers are tensor-bound anyway)
+constexpr int W_MAX_SLOTS = 256;          // k-step slots of one phase and K block (tap lines x slices per line)
 constexpr int w_epi_warps(bool skip) { return skip ? 8 : 16; }
 constexpr int w_threads(bool skip) { return 128 + 32 * w_epi_warps(skip); }
 constexpr int W_PSTAGES = 2;
@@ -74,6 +75,7 @@ struct WArgs {
   int row_sy, row_sx;          // ob > 1: block strides of the row base (ry / ob, rx / ob), 0 = general (ry = rx = 1)
   int ob_shift;                // log2(ob)
   uint32_t pw_magic;           // floor(2^32 / PW) + 1: flat position / PW by one multiply
+  uint32_t aoff[W_MAX_SLOTS];  // A-operand offset (16-byte units) of the i-th k-step slot of a phase: tap line, slice
   int nissue;                  // MMA-issuing warps (2: warps 2 and 3 take alternate M-tiles of a region)
   int msplit;                  // M-tile parts the epilogue warps of one lane quarter split a region into
   int seg_oy[W_MAX_SEGS], seg_ox[W_MAX_SEGS];
@@ -150,6 +152,8 @@ __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint4& a, uint4& 
                : "l"(p));
 }
 
+static_assert(sizeof(WArgs) + 128 <= 4096, "kernel parameter space");
+
 struct WRegion {
   int pi, n, strip, rr;
   int l0;        // M-domain line whose window starts the patch (patch line 0 = input line l0*Jy - top)
@@ -221,7 +225,6 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
   const uint32_t bstep16 = 2u * (uint32_t)N;
   const uint32_t ub16 = (uint32_t)a.ub16;
   const uint32_t tile_step16 = (uint32_t)(a.mode == W_LINE ? a.Jy * a.PW : 128) * ub16;
-  const uint32_t line_step = (uint32_t)a.PW * ub16;
   const int nbst = a.nbst, nblk = a.nblk, glines = a.glines, run = a.run;
   const int total_regions = a.total_regions;
   uint32_t pst = 0, ppar = 0, bst = 0, bpar = 0, as = 0, apar = 0;
@@ -236,24 +239,27 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
     for (int blk = 0; blk < nblk; ++blk) {
       W_TWAIT(1, mbar_wait(&full_p[pst], ppar));
       tc_fence_after();
-      uint32_t da_line = a_lo0 + pst * pstage16 + row0;
+      const uint32_t da_blk = a_lo0 + pst * pstage16 + row0;
+      int s0 = 0;
       for (int l0 = 0; l0 < P.ntl; l0 += glines) {
         W_TWAIT(2, mbar_wait(&full_b[bst], bpar));
         tc_fence_after();
         uint32_t db = b_lo0 + bst * bstage16;
-        const int lend = min(glines, P.ntl - l0);
-        for (int li = 0; li < lend; ++li, da_line += line_step) {
-          uint32_t da = da_line;
+        // one flat walk over the stage's k-step slots: the A offset of slot (tap line, 32-byte slice) comes from
+        // the aoff table in the parameter bank (short tap lines made a nested line / slice loop mostly loop overhead)
+        const int ns = min(glines, P.ntl - l0) * run;
+        const long long t_loop = a.timing ? clock64() : 0;
 #pragma unroll 2
-          for (int sl = 0; sl < run; ++sl) {
+        for (int sl = 0; sl < ns; ++sl) {
+          const uint32_t da = da_blk + a.aoff[s0 + sl];
 #pragma unroll
-            for (int mt = H; mt < T_R; mt += NI)
-              umma_f16_lohi(d_tmem + (uint32_t)(mt * N), da + (uint32_t)mt * tile_step16, a_hi, db, b_hi, idesc, acc, el);
-            acc = 1u;
-            da += 2u;
-            db += bstep16;
-          }
+          for (int mt = H; mt < T_R; mt += NI)
+            umma_f16_lohi(d_tmem + (uint32_t)(mt * N), da + (uint32_t)mt * tile_step16, a_hi, db, b_hi, idesc, acc, el);
+          acc = 1u;
+          db += bstep16;
         }
+        s0 += ns;
+        if (a.timing) tacc[3] += clock64() - t_loop;
         umma_commit_pred(&empty_b[bst], el);
         if (++bst == (uint32_t)nbst) { bst = 0; bpar ^= 1u; }
       }
@@ -283,7 +289,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N;
-  long long tacc[3] = {0, 0, 0};
+  long long tacc[4] = {0, 0, 0, 0};
   const long long t_start = a.timing ? clock64() : 0;
 
   for (int i = tid; i < N; i += w_threads(SKIP)) s_shift[i] = a.shift[i];
@@ -369,7 +375,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
   } else if (warp == 3) {
     // ===================== second MMA issuer (odd M-tiles) =====================
     if (a.nissue == 2) {
-      long long tdummy[3] = {0, 0, 0};
+      long long tdummy[4] = {0, 0, 0, 0};
       switch (a.T_r) {
         case 2: w_issue<2, 2, 1>(a, sP, sB, bars, tmem_base, tdummy); break;
         case 3: w_issue<3, 2, 1>(a, sP, sB, bars, tmem_base, tdummy); break;
@@ -554,7 +560,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     long long* t = a.timing + (size_t)blockIdx.x * 8;
     if (warp == 0) { t[0] = clock64() - t_start; t[1] = tacc[0]; }
     if (warp == 1) t[2] = tacc[0];
-    if (warp == 2) { t[3] = tacc[0]; t[4] = tacc[1]; t[5] = tacc[2]; }
+    if (warp == 2) { t[3] = tacc[0]; t[4] = tacc[1]; t[5] = tacc[2]; t[7] = tacc[3]; }
     if (warp == 4) t[6] = tacc[0];
   }
   tc_fence_before();
@@ -737,6 +743,12 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
   if (sp.mode == W_LINE) a.lines = a.T_r * sp.Jy + a.top + bottom;
   else a.lines = (a.T_r * 128 + a.PW - 1) / a.PW + 1 + a.top + bottom;
   a.box_bytes = (uint32_t)UB * a.PW * a.lines;
+  if (ntl_max * run > W_MAX_SLOTS) {
+    delete wl;
+    set_error("window GEMM: %d tap lines x %d slices exceed the %d-slot offset table", ntl_max, run, W_MAX_SLOTS);
+    return BP_E_UNSUPPORTED;
+  }
+  for (int i = 0; i < ntl_max * run; ++i) a.aoff[i] = (uint32_t)((i / run) * a.PW * (UB / 16) + (i % run) * 2);
   // slack: garbage M rows of the last tile read up to (left + right) units past the box
   a.kb_bytes = (uint32_t)(((size_t)a.box_bytes + (size_t)UB * (a.left + right + 8) + 1023) / 1024 * 1024);
   a.stage_bytes = a.kb_bytes;
@@ -936,16 +948,16 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
     BP_CUDA_TRY(cudaStreamSynchronize(s));
     std::vector<long long> h(8 * 256);
     BP_CUDA_TRY(cudaMemcpy(h.data(), d_timing, sizeof(long long) * 8 * 256, cudaMemcpyDeviceToHost));
-    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int c = 0; c < grid; ++c)
-      for (int q = 0; q < 7; ++q) acc[q] += (double)h[c * 8 + q] / grid;
+      for (int q = 0; q < 8; ++q) acc[q] += (double)h[c * 8 + q] / grid;
     double floor_cyc = 0;
     const long long mm = wconv_mma_count(wl, nb, &floor_cyc);
     fprintf(stderr,
             "[wconv] N=%d T_r=%d ksb=%dx%d nbst=%d mode=%d ub=%d nkb=%d PW=%d lines=%d regions/cta=%.1f mma/cta=%.0f floor=%.0f total=%.0f cyc"
-            " | waits: A-prod %.0f B-prod %.0f mma:tempty %.0f mma:full_p %.0f mma:full_b %.0f epi:tfull %.0f\n",
+            " | waits: A-prod %.0f B-prod %.0f mma:tempty %.0f mma:full_p %.0f mma:full_b %.0f epi:tfull %.0f | mma:loops %.0f\n",
             a.N, a.T_r, a.glines, a.run, a.nbst, a.mode, a.ub16 * 16, a.nkb, a.PW, a.lines, (double)a.total_regions / grid, (double)mm / grid,
-            floor_cyc / grid, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
+            floor_cyc / grid, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]);
   }
   return BP_OK;
 }

@@ -124,7 +124,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tiles", type=int, default=256)
     ap.add_argument("--precision", default=os.environ.get("BARYON_PAINTER_PRECISION", "fp16"))
