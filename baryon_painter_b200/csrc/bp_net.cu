@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <new>
 
@@ -975,7 +976,7 @@ static int cvae_chunk_back(bp_net* net, const float* tiles, const float* latent,
 struct ChunkHooks {
   std::vector<cudaEvent_t>* ready = nullptr;
   std::vector<cudaEvent_t>* done = nullptr;
-  int step = 0;       // tiles per pipeline chunk (<= the plan's chunk capacity); 0 = the plan's chunk
+  const std::vector<int>* bounds = nullptr;   // pipeline chunk c = tiles [bounds[c], bounds[c + 1]); null = the plan's chunks
 };
 
 static int cvae_paint_device(bp_net* net, const float* tiles, const float* latent, int mode, uint64_t seed,
@@ -995,11 +996,17 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
   const size_t lhw = (size_t)net->lh * net->lw;
   net->prior_valid = 0;
   if (net->debug) net->dbg_n = std::min(n, net->chunk);
-  const int step = (hooks && hooks->step > 0) ? std::min(hooks->step, net->chunk) : net->chunk;
-  for (int c0 = 0; c0 < n; c0 += step) {
-    const int nb = std::min(step, n - c0);
+  std::vector<int> plain;
+  if (!(hooks && hooks->bounds)) {
+    for (int c0 = 0; c0 < n; c0 += net->chunk) plain.push_back(c0);
+    plain.push_back(n);
+  }
+  const std::vector<int>& bounds = (hooks && hooks->bounds) ? *hooks->bounds : plain;
+  for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+    const int c0 = bounds[ci], nb = bounds[ci + 1] - c0;
+    BP_REQUIRE(nb > 0 && nb <= net->chunk, BP_E_INVALID, "internal: pipeline chunk of %d tiles", nb);
     float* prior_out = nullptr;
-    if (hooks && hooks->ready) BP_CUDA_TRY(cudaStreamWaitEvent(s, (*hooks->ready)[c0 / step], 0));
+    if (hooks && hooks->ready) BP_CUDA_TRY(cudaStreamWaitEvent(s, (*hooks->ready)[ci], 0));
     rc = cvae_chunk_front(net, tiles, tp, flags, c0, nb, mode != BP_LATENT_GIVEN, s, &prior_out);
     if (rc != BP_OK) return rc;
     const float* lat;
@@ -1014,7 +1021,7 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
     }
     rc = cvae_chunk_back(net, tiles, lat, tp, flags, c0, nb, out + (size_t)c0 * HW, s);
     if (rc != BP_OK) return rc;
-    if (hooks && hooks->done) BP_CUDA_TRY(cudaEventRecord((*hooks->done)[c0 / step], s));
+    if (hooks && hooks->done) BP_CUDA_TRY(cudaEventRecord((*hooks->done)[ci], s));
     if (net->debug) break;  // debug buffers hold one chunk
   }
   if (mode != BP_LATENT_GIVEN) net->prior_valid = n;
@@ -1203,16 +1210,43 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   BP_CUDA_TRY(cudaSetDevice(net->device));
   const size_t HW = (size_t)net->H * net->W, lhw = (size_t)net->lh * net->lw;
   cudaStream_t s = net->stream, sin = net->copy_stream, sout = net->out_stream;
-  // pipeline granularity: small enough that copy-in / compute / copy-out of neighbouring chunks overlap, large enough
-  // that the kernels still fill the machine (BP_HOST_STEP overrides)
+  // pipeline chunks: copy-in / compute / copy-out of neighbouring chunks overlap.  The first chunk's copy-in and
+  // the last chunk's copy-out cannot hide behind anything, so the schedule ramps 16, 48, 64, ..., 64, 48, 16
+  // (BP_HOST_STEP / BP_HOST_EDGE override): the exposed copies shrink to 16 tiles each while the bulk of the tiles
+  // still run in launches that fill the machine
   static const int env_step = getenv("BP_HOST_STEP") ? atoi(getenv("BP_HOST_STEP")) : 64;
+  static const int env_edge = getenv("BP_HOST_EDGE") ? atoi(getenv("BP_HOST_EDGE")) : 16;
   const int step = std::max(1, std::min(net->chunk, env_step));
-  const int nchunks = (n + step - 1) / step;
+  std::vector<int> bounds;
+  {
+    std::vector<int> head, tail;
+    int left = n;
+    const int edge = std::max(1, std::min(env_edge, step));
+    for (int sz = edge; sz < step && left >= 2 * sz + step; sz *= 3) {   // ramp while a full middle chunk remains
+      head.push_back(sz); tail.push_back(sz);
+      left -= 2 * sz;
+    }
+    int c0 = 0;
+    bounds.push_back(0);
+    for (int sz : head) bounds.push_back(c0 += sz);
+    for (; left > 0; left -= std::min(step, left)) bounds.push_back(c0 += std::min(step, left));
+    for (size_t i = tail.size(); i-- > 0;) bounds.push_back(c0 += tail[i]);
+  }
+  const int nchunks = (int)bounds.size() - 1;
+  static const bool trace = getenv("BP_HOST_TRACE") != nullptr;      // per-chunk device timeline on stderr
+  const unsigned evflags = trace ? cudaEventDefault : cudaEventDisableTiming;
+  const auto cpu_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_cpu0 = cpu_now();
+  cudaEvent_t ev_t0 = nullptr;
+  if (trace) {
+    BP_CUDA_TRY(cudaEventCreate(&ev_t0));
+    BP_CUDA_TRY(cudaEventRecord(ev_t0, net->copy_stream));
+  }
   while ((int)net->ev_ready.size() < nchunks) {
     cudaEvent_t a, b, c;
-    BP_CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-    BP_CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-    BP_CUDA_TRY(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&a, evflags));
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&b, evflags));
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&c, evflags));
     net->ev_ready.push_back(a); net->ev_chunk_done.push_back(b); net->ev_out.push_back(c);
   }
   const bool in_pinned = is_pinned(tiles), out_pinned = is_pinned(out);
@@ -1222,7 +1256,7 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   }
   // inputs: chunk by chunk on the copy-in stream (staging a pageable chunk overlaps the device's work on earlier ones)
   for (int c = 0; c < nchunks; ++c) {
-    const size_t c0 = (size_t)c * step, nb = std::min((size_t)step, (size_t)n - c0);
+    const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
     const float* src = tiles + c0 * HW;
     if (!in_pinned) {
       memcpy(net->h_in + c0 * HW, src, sizeof(float) * HW * nb);
@@ -1232,12 +1266,12 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
     BP_CUDA_TRY(cudaEventRecord(net->ev_ready[c], sin));
   }
   ChunkHooks hooks;
-  hooks.ready = &net->ev_ready; hooks.done = &net->ev_chunk_done; hooks.step = step;
+  hooks.ready = &net->ev_ready; hooks.done = &net->ev_chunk_done; hooks.bounds = &bounds;
   int rc = cvae_paint_device(net, net->d_in, net->d_lat, latent_mode, seed, tp, flags, net->d_out, n, s, &hooks);
   if (rc != BP_OK) return rc;
   const int done_chunks = net->debug ? 1 : nchunks;
   for (int c = 0; c < done_chunks; ++c) {
-    const size_t c0 = (size_t)c * step, nb = std::min((size_t)step, (size_t)n - c0);
+    const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
     float* dst = out_pinned ? out + c0 * HW : net->h_out + c0 * HW;
     BP_CUDA_TRY(cudaStreamWaitEvent(sout, net->ev_chunk_done[c], 0));
     BP_CUDA_TRY(cudaMemcpyAsync(dst, net->d_out + c0 * HW, sizeof(float) * HW * nb, cudaMemcpyDeviceToHost, sout));
@@ -1245,14 +1279,26 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   }
   if (!out_pinned) {
     for (int c = 0; c < done_chunks; ++c) {
-      const size_t c0 = (size_t)c * step, nb = std::min((size_t)step, (size_t)n - c0);
+      const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
       BP_CUDA_TRY(cudaEventSynchronize(net->ev_out[c]));
       memcpy(out + c0 * HW, net->h_out + c0 * HW, sizeof(float) * HW * nb);
     }
   }
+  const double t_cpu1 = cpu_now();
   BP_CUDA_TRY(cudaStreamSynchronize(sout));
   BP_CUDA_TRY(cudaStreamSynchronize(s));
   BP_CUDA_TRY(cudaStreamSynchronize(sin));
+  if (trace) {
+    fprintf(stderr, "[host] n=%d chunks=%d: enqueue %.2f ms, total %.2f ms (cpu)\n", n, nchunks, t_cpu1 - t_cpu0, cpu_now() - t_cpu0);
+    for (int c = 0; c < done_chunks; ++c) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, ev_t0, net->ev_ready[c]);
+      cudaEventElapsedTime(&b, ev_t0, net->ev_chunk_done[c]);
+      cudaEventElapsedTime(&d, ev_t0, net->ev_out[c]);
+      fprintf(stderr, "[host]   chunk %d tiles [%d, %d): in %.2f  computed %.2f  out %.2f ms\n", c, bounds[c], bounds[c + 1], a, b, d);
+    }
+    cudaEventDestroy(ev_t0);
+  }
   return BP_OK;
 }
 

@@ -185,15 +185,18 @@ class CVAEPainter(Painter):
         return (self._seed + 0x9E3779B97F4A7C15 * self._calls) & (2 ** 64 - 1)
 
     def _sigmas(self, zs, transform, inverse_transform):
+        """Per-tile sigma(z) of the fused transforms (interpolated on the host in fp64 like the reference,
+        data_transforms.py:52-64) -- once per distinct redshift: a batch is typically one lens plane."""
         s_in = s_out = None
         tp = [1.0, 0.0, 1.0, 0.0]
+        uz, inv = np.unique(np.asarray(zs, np.float64), return_inverse=True)
         if transform:
-            p = [self.transform.gpu_params(self.input_field, float(z)) for z in zs]
-            s_in = np.array([q[1] for q in p], np.float32)
+            p = [self.transform.gpu_params(self.input_field, float(z)) for z in uz]
+            s_in = np.array([q[1] for q in p], np.float32)[inv]
             tp[0], tp[1] = p[0][2], p[0][3]
         if inverse_transform:
-            p = [self.inverse_transform.gpu_params(self.label_fields[0], float(z)) for z in zs]
-            s_out = np.array([q[1] for q in p], np.float32)
+            p = [self.inverse_transform.gpu_params(self.label_fields[0], float(z)) for z in uz]
+            s_out = np.array([q[1] for q in p], np.float32)[inv]
             tp[2], tp[3] = p[0][2], p[0][3]
         return s_in, s_out, tp
 
