@@ -316,6 +316,12 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch: the prologue above, and the weight producer's first copies (static data), may
+  // run while the previous kernel of the stream drains; what that kernel wrote is only touched after this wait.
+  // Dependents of this launch may in turn be scheduled as soon as SMs free up.
+  if (warp != 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (warp == 0) {
     // ===================== patch producer =====================
     if (lane == 0) {
@@ -941,7 +947,17 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
     a.timing = d_timing;
   }
   BP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_LIMIT));
-  k<<<grid, w_threads(skip != nullptr), wl->smem, s>>>(wl->tmap, a);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(w_threads(skip != nullptr)); cfg.dynamicSmemBytes = wl->smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = getenv("BP_V2_NOPDL") == nullptr;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    void* args[2] = {const_cast<CUtensorMap*>(&wl->tmap), &a};
+    BP_CUDA_TRY(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(k), args));
+  }
   launch_counter()++;
   BP_CUDA_TRY(cudaGetLastError());
   if (timing) {

@@ -1,5 +1,7 @@
 #!/bin/bash
+# parity (fp16 CVAE tests) + device / end-to-end throughput
 mkdir -p gpurun_out
-timeout 300 python tools/layer_report.py fp16 2>&1 | grep -v "^CVAE" | head -1
-timeout 600 python bench.py --precision fp16 --tiles 256 --steps 3 --warmup 3 --no-cpu-baseline --profile-layers > gpurun_out/bench_v2.json 2> gpurun_out/bench_v2.err
-cut -c1-200 gpurun_out/bench_v2.json; grep -v "^CVAE" gpurun_out/bench_v2.err | tail -27 | awk '{printf "%s %s %s %s %s | ", $1,$2,$5,$8,$9} NR%3==0{print ""}'; echo
+timeout 600 python -m pytest tests/test_gpu_cvae.py tests/test_gpu_cgan.py -m gpu -x -q 2>&1 | tail -3
+for i in 1 2; do
+timeout 300 python bench.py --precision fp16 --tiles 256 --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('value %.0f  e2e %.0f tiles/s  ms/step %.3f' % (d['value'], d['e2e']['value'], d['ms_per_step']))"
+done
