@@ -463,7 +463,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       if (rc != BP_OK) return rc;
       // several formulations of one layer (pixel packing of the narrow stride-1 convolutions): the issue-cycle
       // model orders them, the device decides -- each one that fits is timed on a full chunk and the fastest kept
-      const int max_tune = getenv("BP_V2_NOTUNE") ? 1 : 8;
+      const int max_tune = getenv("BP_V2_NOTUNE") ? 1 : 20;
       float best_ms = 0.f;
       int built = 0, ci = -1, best_ci = -1;
       // BP_V2_CHOICES="stack.index=candidate,..." replays an earlier run's selection without timing (profilers

@@ -184,11 +184,11 @@ static int make_spec_packed(const Layer& l, int fmt, int Cp, int G, int Jy, WSpe
   sp->ry = Jy; sp->rx = G;
   const int coutp = cout == 1 ? 1 : round_pow2(cout, 8);
   if (cout == 1) {
-    sp->N = std::max(16, Jy * G);
+    sp->N = std::max(16, (Jy * G + 15) / 16 * 16);
     sp->seg_len = G; sp->seg_valid = G;
     for (int jy = 0; jy < Jy; ++jy) sp->segs[0].push_back({jy, 0});
   } else {
-    sp->N = std::max(16, Jy * G * coutp);
+    sp->N = std::max(16, (Jy * G * coutp + 15) / 16 * 16);
     sp->seg_len = coutp; sp->seg_valid = coutp;
     for (int jy = 0; jy < Jy; ++jy)
       for (int jx = 0; jx < G; ++jx) sp->segs[0].push_back({jy, jx});
@@ -274,9 +274,10 @@ int v2_candidates(const Layer& l, int fmt, int Cp, std::vector<WSpec>* out) {
     const int ub = G * Cp * 2;
     if (!(ub == 32 || ub == 64 || ub == 128 || (G == 1 && ub % 128 == 0))) continue;
     if (l.OWF % G) continue;
-    for (int Jy : {1, 2, 4, 8, 16}) {
-      const int N = std::max(16, Jy * G * coutp);
+    for (int Jy : {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16}) {
+      const int N = std::max(16, (Jy * G * coutp + 15) / 16 * 16);     // UMMA N: multiple of 16 (dead columns: zero weights)
       if (N > 128) continue;
+      if ((Jy & (Jy - 1)) != 0 && N - Jy * G * coutp >= 8 && N > 16) continue;   // odd packings only where they fill N
       const bool flat = (G == 1 && Jy == 1);
       const int ntap = (Jy + d.kernel - 1) * (floordiv(G - 1 + d.pad, G) - floordiv(-d.pad, G) + 1);
       const int kst = std::max(1, ub / 32);

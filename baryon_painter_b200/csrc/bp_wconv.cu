@@ -35,8 +35,9 @@ using namespace tc;
 // epilogue warps: four per TMEM lane quarter, two for the residual variants (their 32-register prefetch of the
 // skip input does not fit the 96-register budget of a 640-thread CTA, and those layers are tensor-bound anyway)
 constexpr int W_MAX_SLOTS = 256;          // k-step slots of one phase and K block (tap lines x slices per line)
-constexpr int w_epi_warps(bool skip) { return skip ? 8 : 16; }
-constexpr int w_threads(bool skip) { return 128 + 32 * w_epi_warps(skip); }
+// (`wide` = residual or fp32-plane variant: the register-heavy epilogues keep the 384-thread CTA)
+constexpr int w_epi_warps(bool wide) { return wide ? 8 : 16; }
+constexpr int w_threads(bool wide) { return 128 + 32 * w_epi_warps(wide); }
 constexpr int W_PSTAGES = 2;
 constexpr int W_BSTAGES = 4;              // barrier slots; a layer uses a.nbst <= 4 weight stages
 constexpr int W_MAX_SEGS = 32;
@@ -75,6 +76,7 @@ struct WArgs {
   int row_sy, row_sx;          // ob > 1: block strides of the row base (ry / ob, rx / ob), 0 = general (ry = rx = 1)
   int ob_shift;                // log2(ob)
   uint32_t pw_magic;           // floor(2^32 / PW) + 1: flat position / PW by one multiply
+  uint32_t m_per_img, m_rps;   // same for regions per sample and regions per strip (w_decode)
   uint32_t aoff[W_MAX_SLOTS];  // A-operand offset (16-byte units) of the i-th k-step slot of a phase: tap line, slice
   int nissue;                  // MMA-issuing warps (2: warps 2 and 3 take alternate M-tiles of a region)
   int msplit;                  // M-tile parts the epilogue warps of one lane quarter split a region into
@@ -159,22 +161,24 @@ struct WRegion {
   int l0;        // M-domain line whose window starts the patch (patch line 0 = input line l0*Jy - top)
   int tile0;     // patch-local unit offset of M-tile 0
 };
+// region index -> (phase, sample, strip, region of the strip).  Runs once per region in every warp role, on the
+// MMA issuers' critical path: divisions by multiply-high with host-made reciprocals (exact, range-checked there)
 __device__ __forceinline__ WRegion w_decode(const WArgs& a, int reg) {
   WRegion R;
   const int per_img = a.nstrips * a.regs_per_strip;
   const int per_phase = per_img * a.nb;
-  R.pi = reg / per_phase;
+  R.pi = (reg >= per_phase) + (reg >= 2 * per_phase) + (reg >= 3 * per_phase);       // <= 4 phases
   int rem = reg - R.pi * per_phase;
-  R.n = rem / per_img;
+  R.n = a.m_per_img ? (int)__umulhi((uint32_t)rem, a.m_per_img) : rem;          // reciprocal 0: divisor 1
   rem -= R.n * per_img;
-  R.strip = rem / a.regs_per_strip;
+  R.strip = a.m_rps ? (int)__umulhi((uint32_t)rem, a.m_rps) : rem;
   R.rr = rem - R.strip * a.regs_per_strip;
   if (a.mode == W_LINE) {
     R.l0 = R.rr * a.T_r;
     R.tile0 = 0;
   } else {
     const int f0 = R.rr * a.T_r * 128;
-    R.l0 = f0 / a.PW;
+    R.l0 = (int)__umulhi((uint32_t)f0, a.pw_magic);
     R.tile0 = f0 - R.l0 * a.PW;
   }
   return R;
@@ -272,7 +276,7 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
 }
 
 template <int ACT, bool SKIP, bool OUTF32, int FMT>
-__global__ void __launch_bounds__(w_threads(SKIP), 1)
+__global__ void __launch_bounds__(w_threads(SKIP || OUTF32), 1)
 wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sP = smem;
@@ -292,14 +296,14 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
   long long tacc[4] = {0, 0, 0, 0};
   const long long t_start = a.timing ? clock64() : 0;
 
-  for (int i = tid; i < N; i += w_threads(SKIP)) s_shift[i] = a.shift[i];
+  for (int i = tid; i < N; i += w_threads(SKIP || OUTF32)) s_shift[i] = a.shift[i];
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full_p[s], 1);
       mbar_init(&empty_p[s], a.nissue);
       mbar_init(&tfull[s], a.nissue);
-      mbar_init(&tempty[s], 32 * w_epi_warps(SKIP));
+      mbar_init(&tempty[s], 32 * w_epi_warps(SKIP || OUTF32));
     }
     for (int s = 0; s < W_BSTAGES; ++s) {
       mbar_init(&full_b[s], 1);
@@ -394,7 +398,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     // quarter take every msplit-th M-tile and every (NEW / msplit)-th 16-column chunk.  One thread = one M row; a
     // chunk's two 8-column halves are 16-byte stores (one 32-byte store when both lie in one segment) to
     // row_base + seg_delta[segment] (+ channel).
-    constexpr int NEW = w_epi_warps(SKIP) / 4;
+    constexpr int NEW = w_epi_warps(SKIP || OUTF32) / 4;
     const int q = warp & 3;
     const int cpart = (warp - 4) >> 2;
     const int m = q * 32 + lane;
@@ -901,12 +905,19 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   {
     // split of a region over the epilogue warps of one lane quarter: as many M-tile parts as T_r allows while a
     // warp keeps at most four 16-column chunks of an M-tile
-    const int new_ = w_epi_warps(skip != nullptr) / 4;
+    const int new_ = w_epi_warps(skip != nullptr || out.f32) / 4;
     int ms = 1;
     while (ms * 2 <= new_ && ms * 2 <= a.T_r) ms *= 2;
     while (ms > 1 && ((a.N + 15) / 16 + new_ / ms - 1) / (new_ / ms) > 4) ms /= 2;
     BP_REQUIRE(((a.N + 15) / 16 + new_ / ms - 1) / (new_ / ms) <= 4, BP_E_UNSUPPORTED, "window conv: N = %d too wide", a.N);
     a.msplit = ms;
+  {
+    const unsigned long long per_img = (unsigned long long)a.nstrips * a.regs_per_strip;
+    BP_REQUIRE(a.nphase <= 4 && per_img * (per_img * (unsigned)nb + 1) < (1ull << 32), BP_E_UNSUPPORTED,
+               "window conv: %llu regions per sample x %d samples exceed the 32-bit region arithmetic", per_img, nb);
+    a.m_per_img = per_img > 1 ? (uint32_t)((1ull << 32) / per_img) + 1u : 0u;
+    a.m_rps = a.regs_per_strip > 1 ? (uint32_t)((1ull << 32) / (unsigned)a.regs_per_strip) + 1u : 0u;
+  }
   }
   a.oC = out.f32 ? 1 : out.Cp;
   BP_REQUIRE(!out.f32 || out.C == 1, BP_E_UNSUPPORTED, "window GEMM: fp32 output with %d channels", out.C);
@@ -949,7 +960,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   BP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_LIMIT));
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(w_threads(skip != nullptr)); cfg.dynamicSmemBytes = wl->smem; cfg.stream = s;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(w_threads(skip != nullptr || out.f32)); cfg.dynamicSmemBytes = wl->smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
