@@ -232,6 +232,7 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
   const int nbst = a.nbst, nblk = a.nblk, glines = a.glines, run = a.run;
   const int total_regions = a.total_regions;
   uint32_t pst = 0, ppar = 0, bst = 0, bpar = 0, as = 0, apar = 0;
+  bool pre_ok = false;       // the current weight stage's barrier was already seen complete by an early probe
   for (int reg = blockIdx.x; reg < total_regions; reg += gridDim.x) {
     const WRegion R = w_decode(a, reg);
     const WPhase P = a.phase[R.pi];
@@ -246,15 +247,31 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
       const uint32_t da_blk = a_lo0 + pst * pstage16 + row0;
       int s0 = 0;
       for (int l0 = 0; l0 < P.ntl; l0 += glines) {
-        W_TWAIT(2, mbar_wait(&full_b[bst], bpar));
+        if (!pre_ok) W_TWAIT(2, mbar_wait(&full_b[bst], bpar));
         tc_fence_after();
         uint32_t db = b_lo0 + bst * bstage16;
         // one flat walk over the stage's k-step slots: the A offset of slot (tap line, 32-byte slice) comes from
         // the aoff table in the parameter bank (short tap lines made a nested line / slice loop mostly loop overhead)
         const int ns = min(glines, P.ntl - l0) * run;
         const long long t_loop = a.timing ? clock64() : 0;
+        const int ns1 = ns - min(4, ns >> 1);
 #pragma unroll 2
-        for (int sl = 0; sl < ns; ++sl) {
+        for (int sl = 0; sl < ns1; ++sl) {
+          const uint32_t da = da_blk + a.aoff[s0 + sl];
+#pragma unroll
+          for (int mt = H; mt < T_R; mt += NI)
+            umma_f16_lohi(d_tmem + (uint32_t)(mt * N), da + (uint32_t)mt * tile_step16, a_hi, db, b_hi, idesc, acc, el);
+          acc = 1u;
+          db += bstep16;
+        }
+        // probe the next weight stage's barrier now and look at the answer after the last few slots: when the data
+        // is already there (the usual case) the ~90-cycle round trip of the wait hides behind those MMAs
+        {
+          const uint32_t nb_ = bst + 1u == (uint32_t)nbst ? 0u : bst + 1u;
+          pre_ok = mbar_test(&full_b[nb_], nb_ == 0u ? bpar ^ 1u : bpar);
+        }
+#pragma unroll 2
+        for (int sl = ns1; sl < ns; ++sl) {
           const uint32_t da = da_blk + a.aoff[s0 + sl];
 #pragma unroll
           for (int mt = H; mt < T_R; mt += NI)
