@@ -27,7 +27,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 # every symbol declared in include/baryon_painter_b200.h (checked by tests/test_cabi.py)
 EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destroy", "bp_cvae_paint",
            "bp_cvae_paint_host", "bp_cvae_read_prior", "bp_cgan_paint", "bp_cgan_paint_host",
-           "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize",
+           "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles",
            "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
            "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile", "bp_net_chunk",
            "bp_last_error", "bp_version")
@@ -91,6 +91,7 @@ def load():
     lib.bp_cvae_paint_variance_host.argtypes = [vp, vp, tpp, i32, u64, vp, vp, i32]
     lib.bp_stitch_accumulate.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, f32, vp]
     lib.bp_stitch_finalize.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
+    lib.bp_zoom_tiles.argtypes = [i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp]
     lib.bp_net_set_debug.argtypes = [vp, i32]
     lib.bp_net_read_activation.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
     lib.bp_net_set_profile.argtypes = [vp, i32]
@@ -234,10 +235,13 @@ class Net:
                                                  var.ctypes.data, n))
         return mean, var
 
-    def cgan_paint_host(self, tiles, tparams, flags):
+    def cgan_paint_host(self, tiles, tparams, flags, out=None):
         n = tiles.shape[0]
         tiles = np.ascontiguousarray(tiles, np.float32)
-        out = np.empty((n, *self.tile_hw), np.float32)
+        if out is None:
+            out = np.empty((n, *self.tile_hw), np.float32)
+        elif out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (n, *self.tile_hw):
+            raise ValueError("out must be a C-contiguous float32 array of shape %r" % ((n, *self.tile_hw),))
         tp, keep = self._tp(*tparams)
         check(load().bp_cgan_paint_host(self.handle, tiles.ctypes.data, ctypes.byref(tp), flags, out.ctypes.data, n))
         return out
@@ -284,6 +288,16 @@ def stitch_accumulate(num_ptr, den_ptr, n_pixel_plane, tiles_ptr, origins_ptr, n
 
 def stitch_finalize(num_ptr, den_ptr, plane_ptr, n_pixels, stream=0):
     check(load().bp_stitch_finalize(num_ptr, den_ptr, plane_ptr, int(n_pixels), stream))
+
+
+ZOOM_MODES = {"reflect": 0, "mirror": 1}       # BP_ZOOM_REFLECT / BP_ZOOM_MIRROR
+
+
+def zoom_tiles(device, plane_ptr, plane_h, plane_w, origins_ptr, side, n, out_side, mode, out_ptr, stream=0):
+    """Device pointers: float32 plane [plane_h, plane_w], int32 origins [n,2] (row0, col0 of each periodic
+    side x side crop), float32 out [n,out_side,out_side] = scipy.ndimage.zoom(crop, out_side/side, mode=mode)."""
+    check(load().bp_zoom_tiles(int(device), plane_ptr, int(plane_h), int(plane_w), origins_ptr, int(side), int(n),
+                               int(out_side), ZOOM_MODES[mode], out_ptr, stream))
 
 
 def pinned_empty(shape, dtype=np.float32):

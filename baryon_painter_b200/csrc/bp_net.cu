@@ -1029,7 +1029,7 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
 }
 
 static int cgan_paint_device(bp_net* net, const float* tiles, const bp_transform_params* tp, int flags, float* out,
-                             int n, cudaStream_t s) {
+                             int n, cudaStream_t s, const ChunkHooks* hooks = nullptr) {
   BP_REQUIRE(net && net->kind == NET_CGAN, BP_E_INVALID, "not a CGAN network");
   BP_REQUIRE(n >= 0 && n <= net->max_batch, BP_E_INVALID, "batch %d exceeds max_batch %d", n, net->max_batch);
   if (n == 0) return BP_OK;
@@ -1040,8 +1040,21 @@ static int cgan_paint_device(bp_net* net, const float* tiles, const bp_transform
   const size_t HW = (size_t)net->H * net->W;
   const int mb = net->max_batch;
   if (net->debug) net->dbg_n = std::min(n, net->chunk);
-  for (int c0 = 0; c0 < n; c0 += net->chunk) {
-    const int nb = std::min(net->chunk, n - c0);
+  std::vector<int> plain;
+  if (!(hooks && hooks->bounds)) {
+    for (int c0 = 0; c0 < n; c0 += net->chunk) plain.push_back(c0);
+    plain.push_back(n);
+  }
+  const std::vector<int>& bounds = (hooks && hooks->bounds) ? *hooks->bounds : plain;
+  struct DoneGuard {                       // records done[ci] on every way out of a loop iteration
+    const ChunkHooks* h; size_t ci; cudaStream_t s;
+    ~DoneGuard() { if (h && h->done) cudaEventRecord((*h->done)[ci], s); }
+  };
+  for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+    const int c0 = bounds[ci], nb = bounds[ci + 1] - c0;
+    BP_REQUIRE(nb > 0 && nb <= net->chunk, BP_E_INVALID, "internal: pipeline chunk of %d tiles", nb);
+    if (hooks && hooks->ready) BP_CUDA_TRY(cudaStreamWaitEvent(s, (*hooks->ready)[ci], 0));
+    DoneGuard guard{hooks, ci, s};
     if (net->v2.built) {
       PostOp post2;
       if (flags & BP_FLAG_INVERSE) {
@@ -1078,6 +1091,111 @@ static int cgan_paint_device(bp_net* net, const float* tiles, const bp_transform
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
+// page-locked (or otherwise CUDA-registered) host memory can be the source / target of an async copy directly
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Host-buffer painting, shared by both painters: copy-in / compute / copy-out of neighbouring pipeline chunks
+// overlap on three streams.  `run(hooks)` enqueues the device work, waiting for hooks.ready[c] before chunk c and
+// recording hooks.done[c] after it.
+template <class Run>
+static int paint_host_pipelined(bp_net* net, const float* tiles, float* out, int n, Run run) {
+  const size_t HW = (size_t)net->H * net->W;
+  cudaStream_t s = net->stream, sin = net->copy_stream, sout = net->out_stream;
+  // pipeline chunks: copy-in / compute / copy-out of neighbouring chunks overlap.  The first chunk's copy-in and
+  // the last chunk's copy-out cannot hide behind anything, so the schedule ramps 16, 48, 64, ..., 64, 48, 16
+  // (BP_HOST_STEP / BP_HOST_EDGE override): the exposed copies shrink to 16 tiles each while the bulk of the tiles
+  // still run in launches that fill the machine
+  static const int env_step = getenv("BP_HOST_STEP") ? atoi(getenv("BP_HOST_STEP")) : 64;
+  static const int env_edge = getenv("BP_HOST_EDGE") ? atoi(getenv("BP_HOST_EDGE")) : 16;
+  const int step = std::max(1, std::min(net->chunk, env_step));
+  std::vector<int> bounds;
+  {
+    std::vector<int> head, tail;
+    int left = n;
+    const int edge = std::max(1, std::min(env_edge, step));
+    for (int sz = edge; sz < step && left >= 2 * sz + step; sz *= 3) {   // ramp while a full middle chunk remains
+      head.push_back(sz); tail.push_back(sz);
+      left -= 2 * sz;
+    }
+    int c0 = 0;
+    bounds.push_back(0);
+    for (int sz : head) bounds.push_back(c0 += sz);
+    for (; left > 0; left -= std::min(step, left)) bounds.push_back(c0 += std::min(step, left));
+    for (size_t i = tail.size(); i-- > 0;) bounds.push_back(c0 += tail[i]);
+  }
+  const int nchunks = (int)bounds.size() - 1;
+  static const bool trace = getenv("BP_HOST_TRACE") != nullptr;      // per-chunk device timeline on stderr
+  const unsigned evflags = trace ? cudaEventDefault : cudaEventDisableTiming;
+  const auto cpu_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_cpu0 = cpu_now();
+  cudaEvent_t ev_t0 = nullptr;
+  if (trace) {
+    BP_CUDA_TRY(cudaEventCreate(&ev_t0));
+    BP_CUDA_TRY(cudaEventRecord(ev_t0, net->copy_stream));
+  }
+  while ((int)net->ev_ready.size() < nchunks) {
+    cudaEvent_t a, b, c;
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&a, evflags));
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&b, evflags));
+    BP_CUDA_TRY(cudaEventCreateWithFlags(&c, evflags));
+    net->ev_ready.push_back(a); net->ev_chunk_done.push_back(b); net->ev_out.push_back(c);
+  }
+  const bool in_pinned = is_pinned(tiles), out_pinned = is_pinned(out);
+  // inputs: chunk by chunk on the copy-in stream (staging a pageable chunk overlaps the device's work on earlier ones)
+  for (int c = 0; c < nchunks; ++c) {
+    const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
+    const float* src = tiles + c0 * HW;
+    if (!in_pinned) {
+      memcpy(net->h_in + c0 * HW, src, sizeof(float) * HW * nb);
+      src = net->h_in + c0 * HW;
+    }
+    BP_CUDA_TRY(cudaMemcpyAsync(net->d_in + c0 * HW, src, sizeof(float) * HW * nb, cudaMemcpyHostToDevice, sin));
+    BP_CUDA_TRY(cudaEventRecord(net->ev_ready[c], sin));
+  }
+  ChunkHooks hooks;
+  hooks.ready = &net->ev_ready; hooks.done = &net->ev_chunk_done; hooks.bounds = &bounds;
+  int rc = run(hooks);
+  if (rc != BP_OK) return rc;
+  const int done_chunks = net->debug ? 1 : nchunks;
+  for (int c = 0; c < done_chunks; ++c) {
+    const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
+    float* dst = out_pinned ? out + c0 * HW : net->h_out + c0 * HW;
+    BP_CUDA_TRY(cudaStreamWaitEvent(sout, net->ev_chunk_done[c], 0));
+    BP_CUDA_TRY(cudaMemcpyAsync(dst, net->d_out + c0 * HW, sizeof(float) * HW * nb, cudaMemcpyDeviceToHost, sout));
+    BP_CUDA_TRY(cudaEventRecord(net->ev_out[c], sout));
+  }
+  if (!out_pinned) {
+    for (int c = 0; c < done_chunks; ++c) {
+      const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
+      BP_CUDA_TRY(cudaEventSynchronize(net->ev_out[c]));
+      memcpy(out + c0 * HW, net->h_out + c0 * HW, sizeof(float) * HW * nb);
+    }
+  }
+  const double t_cpu1 = cpu_now();
+  BP_CUDA_TRY(cudaStreamSynchronize(sout));
+  BP_CUDA_TRY(cudaStreamSynchronize(s));
+  BP_CUDA_TRY(cudaStreamSynchronize(sin));
+  if (trace) {
+    fprintf(stderr, "[host] n=%d chunks=%d: enqueue %.2f ms, total %.2f ms (cpu)\n", n, nchunks, t_cpu1 - t_cpu0, cpu_now() - t_cpu0);
+    for (int c = 0; c < done_chunks; ++c) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, ev_t0, net->ev_ready[c]);
+      cudaEventElapsedTime(&b, ev_t0, net->ev_chunk_done[c]);
+      cudaEventElapsedTime(&d, ev_t0, net->ev_out[c]);
+      fprintf(stderr, "[host]   chunk %d tiles [%d, %d): in %.2f  computed %.2f  out %.2f ms\n", c, bounds[c], bounds[c + 1], a, b, d);
+    }
+    cudaEventDestroy(ev_t0);
+  }
+  return BP_OK;
+}
+
 extern "C" {
 
 int bp_version(void) { return BP_VERSION; }
@@ -1186,14 +1304,6 @@ int bp_cgan_paint(bp_net* net, const float* tiles, const bp_transform_params* tp
   return cgan_paint_device(net, tiles, tp, flags, out, n, (cudaStream_t)stream);
 }
 
-static bool is_pinned(const void* p) {
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return at.type == cudaMemoryTypeHost;
-}
 
 // Host buffers in, host buffers out.  The batch is processed in the network's chunks on three streams:
 // copy-in (H2D of chunk c+1), compute (chunk c), copy-out (D2H of chunk c-1), chained by events, so PCIe traffic in
@@ -1208,98 +1318,15 @@ int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int
   BP_REQUIRE(tiles && out, BP_E_INVALID, "null tile pointer");
   BP_REQUIRE(latent_mode == BP_LATENT_SEED || latent != nullptr, BP_E_INVALID, "latent/eps array missing");
   BP_CUDA_TRY(cudaSetDevice(net->device));
-  const size_t HW = (size_t)net->H * net->W, lhw = (size_t)net->lh * net->lw;
-  cudaStream_t s = net->stream, sin = net->copy_stream, sout = net->out_stream;
-  // pipeline chunks: copy-in / compute / copy-out of neighbouring chunks overlap.  The first chunk's copy-in and
-  // the last chunk's copy-out cannot hide behind anything, so the schedule ramps 16, 48, 64, ..., 64, 48, 16
-  // (BP_HOST_STEP / BP_HOST_EDGE override): the exposed copies shrink to 16 tiles each while the bulk of the tiles
-  // still run in launches that fill the machine
-  static const int env_step = getenv("BP_HOST_STEP") ? atoi(getenv("BP_HOST_STEP")) : 64;
-  static const int env_edge = getenv("BP_HOST_EDGE") ? atoi(getenv("BP_HOST_EDGE")) : 16;
-  const int step = std::max(1, std::min(net->chunk, env_step));
-  std::vector<int> bounds;
-  {
-    std::vector<int> head, tail;
-    int left = n;
-    const int edge = std::max(1, std::min(env_edge, step));
-    for (int sz = edge; sz < step && left >= 2 * sz + step; sz *= 3) {   // ramp while a full middle chunk remains
-      head.push_back(sz); tail.push_back(sz);
-      left -= 2 * sz;
-    }
-    int c0 = 0;
-    bounds.push_back(0);
-    for (int sz : head) bounds.push_back(c0 += sz);
-    for (; left > 0; left -= std::min(step, left)) bounds.push_back(c0 += std::min(step, left));
-    for (size_t i = tail.size(); i-- > 0;) bounds.push_back(c0 += tail[i]);
-  }
-  const int nchunks = (int)bounds.size() - 1;
-  static const bool trace = getenv("BP_HOST_TRACE") != nullptr;      // per-chunk device timeline on stderr
-  const unsigned evflags = trace ? cudaEventDefault : cudaEventDisableTiming;
-  const auto cpu_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t_cpu0 = cpu_now();
-  cudaEvent_t ev_t0 = nullptr;
-  if (trace) {
-    BP_CUDA_TRY(cudaEventCreate(&ev_t0));
-    BP_CUDA_TRY(cudaEventRecord(ev_t0, net->copy_stream));
-  }
-  while ((int)net->ev_ready.size() < nchunks) {
-    cudaEvent_t a, b, c;
-    BP_CUDA_TRY(cudaEventCreateWithFlags(&a, evflags));
-    BP_CUDA_TRY(cudaEventCreateWithFlags(&b, evflags));
-    BP_CUDA_TRY(cudaEventCreateWithFlags(&c, evflags));
-    net->ev_ready.push_back(a); net->ev_chunk_done.push_back(b); net->ev_out.push_back(c);
-  }
-  const bool in_pinned = is_pinned(tiles), out_pinned = is_pinned(out);
+  const size_t lhw = (size_t)net->lh * net->lw;
+  cudaStream_t s = net->stream, sin = net->copy_stream;
   if (latent_mode != BP_LATENT_SEED) {
     memcpy(net->h_lat, latent, sizeof(float) * lhw * n);
     BP_CUDA_TRY(cudaMemcpyAsync(net->d_lat, net->h_lat, sizeof(float) * lhw * n, cudaMemcpyHostToDevice, sin));
   }
-  // inputs: chunk by chunk on the copy-in stream (staging a pageable chunk overlaps the device's work on earlier ones)
-  for (int c = 0; c < nchunks; ++c) {
-    const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
-    const float* src = tiles + c0 * HW;
-    if (!in_pinned) {
-      memcpy(net->h_in + c0 * HW, src, sizeof(float) * HW * nb);
-      src = net->h_in + c0 * HW;
-    }
-    BP_CUDA_TRY(cudaMemcpyAsync(net->d_in + c0 * HW, src, sizeof(float) * HW * nb, cudaMemcpyHostToDevice, sin));
-    BP_CUDA_TRY(cudaEventRecord(net->ev_ready[c], sin));
-  }
-  ChunkHooks hooks;
-  hooks.ready = &net->ev_ready; hooks.done = &net->ev_chunk_done; hooks.bounds = &bounds;
-  int rc = cvae_paint_device(net, net->d_in, net->d_lat, latent_mode, seed, tp, flags, net->d_out, n, s, &hooks);
-  if (rc != BP_OK) return rc;
-  const int done_chunks = net->debug ? 1 : nchunks;
-  for (int c = 0; c < done_chunks; ++c) {
-    const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
-    float* dst = out_pinned ? out + c0 * HW : net->h_out + c0 * HW;
-    BP_CUDA_TRY(cudaStreamWaitEvent(sout, net->ev_chunk_done[c], 0));
-    BP_CUDA_TRY(cudaMemcpyAsync(dst, net->d_out + c0 * HW, sizeof(float) * HW * nb, cudaMemcpyDeviceToHost, sout));
-    BP_CUDA_TRY(cudaEventRecord(net->ev_out[c], sout));
-  }
-  if (!out_pinned) {
-    for (int c = 0; c < done_chunks; ++c) {
-      const size_t c0 = (size_t)bounds[c], nb = (size_t)(bounds[c + 1] - bounds[c]);
-      BP_CUDA_TRY(cudaEventSynchronize(net->ev_out[c]));
-      memcpy(out + c0 * HW, net->h_out + c0 * HW, sizeof(float) * HW * nb);
-    }
-  }
-  const double t_cpu1 = cpu_now();
-  BP_CUDA_TRY(cudaStreamSynchronize(sout));
-  BP_CUDA_TRY(cudaStreamSynchronize(s));
-  BP_CUDA_TRY(cudaStreamSynchronize(sin));
-  if (trace) {
-    fprintf(stderr, "[host] n=%d chunks=%d: enqueue %.2f ms, total %.2f ms (cpu)\n", n, nchunks, t_cpu1 - t_cpu0, cpu_now() - t_cpu0);
-    for (int c = 0; c < done_chunks; ++c) {
-      float a = 0, b = 0, d = 0;
-      cudaEventElapsedTime(&a, ev_t0, net->ev_ready[c]);
-      cudaEventElapsedTime(&b, ev_t0, net->ev_chunk_done[c]);
-      cudaEventElapsedTime(&d, ev_t0, net->ev_out[c]);
-      fprintf(stderr, "[host]   chunk %d tiles [%d, %d): in %.2f  computed %.2f  out %.2f ms\n", c, bounds[c], bounds[c + 1], a, b, d);
-    }
-    cudaEventDestroy(ev_t0);
-  }
-  return BP_OK;
+  return paint_host_pipelined(net, tiles, out, n, [&](const ChunkHooks& hooks) {
+    return cvae_paint_device(net, net->d_in, net->d_lat, latent_mode, seed, tp, flags, net->d_out, n, s, &hooks);
+  });
 }
 
 int bp_cgan_paint_host(bp_net* net, const float* tiles, const bp_transform_params* tp, int flags, float* out,
@@ -1309,16 +1336,10 @@ int bp_cgan_paint_host(bp_net* net, const float* tiles, const bp_transform_param
   if (n == 0) return BP_OK;
   BP_REQUIRE(tiles && out, BP_E_INVALID, "null tile pointer");
   BP_CUDA_TRY(cudaSetDevice(net->device));
-  const size_t HW = (size_t)net->H * net->W;
   cudaStream_t s = net->stream;
-  memcpy(net->h_in, tiles, sizeof(float) * HW * n);
-  BP_CUDA_TRY(cudaMemcpyAsync(net->d_in, net->h_in, sizeof(float) * HW * n, cudaMemcpyHostToDevice, s));
-  int rc = cgan_paint_device(net, net->d_in, tp, flags, net->d_out, n, s);
-  if (rc != BP_OK) return rc;
-  BP_CUDA_TRY(cudaMemcpyAsync(net->h_out, net->d_out, sizeof(float) * HW * n, cudaMemcpyDeviceToHost, s));
-  BP_CUDA_TRY(cudaStreamSynchronize(s));
-  memcpy(out, net->h_out, sizeof(float) * HW * n);
-  return BP_OK;
+  return paint_host_pipelined(net, tiles, out, n, [&](const ChunkHooks& hooks) {
+    return cgan_paint_device(net, net->d_in, tp, flags, net->d_out, n, s, &hooks);
+  });
 }
 
 int bp_cvae_read_prior(bp_net* net, float* z_mu, float* z_log_var, int n) {

@@ -128,12 +128,14 @@ __device__ __forceinline__ uint32_t w_finish_pair(unsigned long long x2, int act
   float x, y;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(x2));
   uint32_t r;
-  if (ACT == BP_ACT_RELU) {
+  // the generic instantiation (ACT = -1) branches once per pair on the warp-uniform runtime code, ReLU and "none"
+  // first (the closing convolution of a residual block has no activation of its own)
+  if (ACT == BP_ACT_RELU || (ACT == -1 && act == BP_ACT_RELU)) {
     if (FMT == 0) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
     else asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
     return r;
   }
-  if (ACT != BP_ACT_NONE) {
+  if (ACT != BP_ACT_NONE && !(ACT == -1 && act == BP_ACT_NONE)) {
     x = w_act<ACT>(x, act, p);
     y = w_act<ACT>(y, act, p);
   }
@@ -889,6 +891,8 @@ static WKernel pick_kernel_fmt(int act, bool skip, bool f32) {
     return skip ? wconv_kernel<BP_ACT_RELU, true, false, FMT> : wconv_kernel<BP_ACT_RELU, false, false, FMT>;
   if ((act == BP_ACT_PRELU || act == BP_ACT_LEAKY) && !skip)
     return f32 ? wconv_kernel<BP_ACT_PRELU, false, true, FMT> : wconv_kernel<BP_ACT_PRELU, false, false, FMT>;
+  if ((act == BP_ACT_PRELU || act == BP_ACT_LEAKY) && !f32)          // LeakyReLU after the residual add (CGAN blocks)
+    return wconv_kernel<BP_ACT_PRELU, true, false, FMT>;
   if (skip) return f32 ? nullptr : wconv_kernel<-1, true, false, FMT>;
   return f32 ? wconv_kernel<-1, false, true, FMT> : wconv_kernel<-1, false, false, FMT>;
 }

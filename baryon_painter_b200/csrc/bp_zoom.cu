@@ -1,0 +1,186 @@
+// Tile extraction for the lightcone loop on the device:
+//   periodic crop of a mass / delta plane  (reference process_SLICS.py:68-83, get_tile)
+//   + cubic-spline resampling to the painter's tile size  (reference :200, :213: scipy.ndimage.zoom(tile,
+//     zoom=n_pixel_tile / side, mode="reflect" | "mirror"), i.e. order 3, prefilter on, grid_mode off).
+// The reference runs both on one host core per tile; here a batch of tiles is cropped, prefiltered and resampled
+// by three small kernels and stays on the device for the painter.
+//
+// scipy's algorithm, restated (scipy/ndimage/src/ni_splines.c, ni_interpolation.c; oracle/zoom_oracle.py is the
+// numpy restatement the tests pin against scipy itself):
+//   1. B-spline coefficients: along each axis, c *= 6; causal recursion c[i] += z c[i-1] and anticausal recursion
+//      c[i] = z (c[i+1] - c[i]) with the pole z = sqrt(3) - 2, started from the exact sums of the chosen boundary
+//      extension (mirror: d c b | a b c d | c b a,  reflect: d c b a | a b c d | d c b a); float64 throughout.
+//   2. output sample o reads the input coordinate o (n_in - 1)/(n_out - 1); the four cubic B-spline weights of its
+//      fractional part multiply coefficients floor(x) - 1 .. floor(x) + 2, out-of-range indices folded by the same
+//      boundary extension; float64 accumulation, result rounded to float32.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "bp_common.h"
+
+namespace bp {
+
+constexpr double kPole = -0.26794919243112270647;      // sqrt(3) - 2
+
+// ---- crop with wrap-around -> float64 ---------------------------------------------------------------
+__global__ void zoom_crop_kernel(const float* __restrict__ plane, int ph, int pw, const int* __restrict__ origins, int side,
+                                 double* __restrict__ work) {
+  const int n = blockIdx.z;
+  const int r0 = origins[2 * n], c0 = origins[2 * n + 1];
+  const int y = blockIdx.y;
+  int yy = (r0 + y) % ph;
+  if (yy < 0) yy += ph;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < side; x += gridDim.x * blockDim.x) {
+    int xx = (c0 + x) % pw;
+    if (xx < 0) xx += pw;
+    work[((size_t)n * side + y) * side + x] = (double)plane[(size_t)yy * pw + xx];
+  }
+}
+
+// ---- spline prefilter along one axis: one thread per line ------------------------------------------------
+// element i of line l of tile n: work[n*side*side + l*line_stride + i*elem_stride]
+__global__ void zoom_filter_kernel(double* __restrict__ work, int side, int ntiles, long long line_stride, long long elem_stride,
+                                   int mirror) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)ntiles * side) return;
+  const int n = (int)(t / side), l = (int)(t % side);
+  double* c = work + (size_t)n * side * side + (size_t)l * line_stride;
+  const int len = side;
+  if (len < 2) return;
+  const double z = kPole;
+#define C(i) c[(size_t)(i) * elem_stride]
+  for (int i = 0; i < len; ++i) C(i) *= 6.0;               // (1 - z)(1 - 1/z)
+  // causal initialisation
+  if (mirror) {
+    const double z_n_1 = pow(z, (double)(len - 1));
+    double z_i = z, s = C(0) + z_n_1 * C(len - 1);
+    for (int i = 1; i < len - 1; ++i) {
+      s += z_i * (C(i) + z_n_1 * C(len - 1 - i));
+      z_i *= z;
+    }
+    C(0) = s / (1.0 - z_n_1 * z_n_1);
+  } else {
+    const double z_n = pow(z, (double)len);
+    const double c0 = C(0);
+    double z_i = z, s = C(0) + z_n * C(len - 1);
+    for (int i = 1; i < len; ++i) {
+      s += z_i * (C(i) + z_n * C(len - 1 - i));
+      z_i *= z;
+    }
+    C(0) = s * (z / (1.0 - z_n * z_n)) + c0;
+  }
+  for (int i = 1; i < len; ++i) C(i) += z * C(i - 1);
+  // anticausal initialisation
+  if (mirror) C(len - 1) = (z * C(len - 2) + C(len - 1)) * z / (z * z - 1.0);
+  else C(len - 1) *= z / (z - 1.0);
+  for (int i = len - 2; i >= 0; --i) C(i) = z * (C(i + 1) - C(i));
+#undef C
+}
+
+__device__ __forceinline__ int zoom_fold(int idx, int len, int mirror) {
+  if (idx >= 0 && idx < len) return idx;
+  if (len <= 1) return 0;
+  if (mirror) {
+    const int s2 = 2 * len - 2;
+    if (idx < 0) {
+      idx = s2 * (-idx / s2) + idx;
+      return idx <= 1 - len ? idx + s2 : -idx;
+    }
+    idx -= s2 * (idx / s2);
+    return idx >= len ? s2 - idx : idx;
+  }
+  const int s2 = 2 * len;
+  if (idx < 0) {
+    if (idx < -s2) idx += s2 * (-idx / s2);
+    return idx < -len ? idx + s2 : -idx - 1;
+  }
+  idx -= s2 * (idx / s2);
+  return idx >= len ? s2 - idx - 1 : idx;
+}
+
+__device__ __forceinline__ void zoom_weights(double x, int* start, double w[4]) {
+  const double f = floor(x);
+  const double t = x - f;
+  *start = (int)f - 1;
+  const double t1 = 1.0 - t;
+  w[0] = t1 * t1 * t1 / 6.0;
+  w[1] = (t * t * (t - 2.0) * 3.0 + 4.0) / 6.0;
+  w[2] = (t1 * t1 * (t1 - 2.0) * 3.0 + 4.0) / 6.0;
+  w[3] = t * t * t / 6.0;
+}
+
+// ---- evaluation: one thread per output pixel -----------------------------------------------------------
+__global__ void zoom_eval_kernel(const double* __restrict__ work, int side, int out_side, int mirror, float* __restrict__ out) {
+  const int n = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= out_side) return;
+  const double scale = out_side > 1 ? (double)(side - 1) / (double)(out_side - 1) : 0.0;
+  int sy, sx;
+  double wy[4], wx[4];
+  zoom_weights((double)oy * scale, &sy, wy);
+  zoom_weights((double)ox * scale, &sx, wx);
+  const double* c = work + (size_t)n * side * side;
+  int ix[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) ix[b] = zoom_fold(sx + b, side, mirror);
+  double acc = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double* row = c + (size_t)zoom_fold(sy + a, side, mirror) * side;
+    double r = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r += wx[b] * row[ix[b]];
+    acc += wy[a] * r;
+  }
+  out[((size_t)n * out_side + oy) * out_side + ox] = (float)acc;
+}
+
+// grow-only float64 workspace per device
+static double* zoom_workspace(int device, size_t elems) {
+  static std::mutex mu;
+  static std::vector<std::pair<double*, size_t>> ws(64, {nullptr, 0});
+  std::lock_guard<std::mutex> lock(mu);
+  auto& w = ws[device & 63];
+  if (w.second < elems) {
+    if (w.first) cudaFree(w.first);
+    w.first = nullptr; w.second = 0;
+    if (cudaMalloc(&w.first, elems * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    w.second = elems;
+  }
+  return w.first;
+}
+
+}  // namespace bp
+
+using namespace bp;
+
+extern "C" int bp_zoom_tiles(int device, const float* plane, int plane_h, int plane_w, const int* origins, int side, int n,
+                             int out_side, int mode, float* out, void* stream) {
+  BP_REQUIRE(plane && origins && out, BP_E_INVALID, "zoom_tiles: null pointer");
+  BP_REQUIRE(plane_h > 0 && plane_w > 0 && side >= 2 && out_side >= 1 && n >= 0, BP_E_INVALID,
+             "zoom_tiles: bad geometry (plane %dx%d, side %d, out %d, n %d)", plane_h, plane_w, side, out_side, n);
+  BP_REQUIRE(mode == BP_ZOOM_REFLECT || mode == BP_ZOOM_MIRROR, BP_E_UNSUPPORTED, "zoom_tiles: boundary mode %d", mode);
+  if (n == 0) return BP_OK;
+  BP_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* work = zoom_workspace(device, (size_t)n * side * side);
+  BP_REQUIRE(work, BP_E_NOMEM, "zoom_tiles: %zu bytes of workspace", (size_t)n * side * side * sizeof(double));
+  const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
+  zoom_crop_kernel<<<dim3((side + 255) / 256, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
+  const long long lines = (long long)n * side;
+  const int fb = 64;
+  // along x (lines = rows), then along y (lines = columns): scipy filters axis by axis and the recursions commute
+  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, (long long)side, 1LL, mirror);
+  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, 1LL, (long long)side, mirror);
+  zoom_eval_kernel<<<dim3((out_side + 127) / 128, out_side, n), 128, 0, s>>>(work, side, out_side, mirror, out);
+  launch_counter() += 4;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}

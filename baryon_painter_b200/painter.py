@@ -466,7 +466,9 @@ class CGANPainter(Painter):
         if state_dict is not None:
             self.model.load_state_dict(state_dict)
 
-    def paint_batch(self, tiles, z=0.0, transform=True, inverse_transform=True):
+    def paint_batch(self, tiles, z=0.0, transform=True, inverse_transform=True, out=None):
+        """Paint N tiles; ``z`` scalar or (N,).  ``out``: optional float32 (N,H,W) result buffer (page-locked
+        ``tiles`` / ``out`` are transferred by DMA, overlapped with the kernels)."""
         tiles = np.asarray(tiles)
         n = tiles.shape[0]
         if tuple(tiles.shape[-2:]) != self.model.tile_hw:
@@ -475,21 +477,25 @@ class CGANPainter(Painter):
         tiles = np.ascontiguousarray(tiles.reshape(n, *self.model.tile_hw), np.float32)
         tp = [1.0, 0.0, 1.0, 0.0]
         s_in = s_out = None
+        uz, inv = np.unique(zs, return_inverse=True)          # sigma(z) once per distinct redshift
         if transform:
-            p = [self.transform.gpu_params(self.input_field, float(zz)) for zz in zs]
-            s_in, tp[0], tp[1] = np.array([q[1] for q in p], np.float32), p[0][2], p[0][3]
+            p = [self.transform.gpu_params(self.input_field, float(zz)) for zz in uz]
+            s_in, tp[0], tp[1] = np.array([q[1] for q in p], np.float32)[inv], p[0][2], p[0][3]
         if inverse_transform:
-            p = [self.inverse_transform.gpu_params(self.label_fields[0], float(zz)) for zz in zs]
-            s_out, tp[2], tp[3] = np.array([q[1] for q in p], np.float32), p[0][2], p[0][3]
+            p = [self.inverse_transform.gpu_params(self.label_fields[0], float(zz)) for zz in uz]
+            s_out, tp[2], tp[3] = np.array([q[1] for q in p], np.float32)[inv], p[0][2], p[0][3]
         flags = (_lib.BP_FLAG_TRANSFORM if transform else 0) | (_lib.BP_FLAG_INVERSE if inverse_transform else 0)
         aux = (zs - self.z_shift).astype(np.float32)
-        out = np.empty((n, *self.model.tile_hw), np.float32)
+        if out is None:
+            out = np.empty((n, *self.model.tile_hw), np.float32)
+        elif out.shape != (n, *self.model.tile_hw) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape %r" % ((n, *self.model.tile_hw),))
         mb = self.model.max_batch
         for i0 in range(0, n, mb):
             sl = slice(i0, min(n, i0 + mb))
-            out[sl] = self.model.net.cgan_paint_host(
+            self.model.net.cgan_paint_host(
                 tiles[sl], (None if s_in is None else s_in[sl], None if s_out is None else s_out[sl], aux[sl], *tp),
-                flags)
+                flags, out=out[sl])
         return out if inverse_transform else out.reshape(n, 1, *out.shape[1:])
 
     def paint(self, input, z=0.0, transform=True, inverse_transform=True):

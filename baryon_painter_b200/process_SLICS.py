@@ -99,16 +99,44 @@ class DeviceBackend:
         z = self.torch.zeros((2, n_pixel_plane, n_pixel_plane), dtype=self.torch.float64, device=self.device)
         return z
 
+    def extract_tiles(self, plane, shifts, tile_relative_size, n_pixel_tile, mode, expansion_factor=1):
+        """``get_tile`` + ``scipy.ndimage.zoom(tile, n_pixel_tile / side, mode=mode)`` for a list of shifts, on the
+        device (csrc/bp_zoom.cu): (n, n_pixel_tile, n_pixel_tile) float32 device tensor.  The plane is uploaded once
+        per plane; reference process_SLICS.py:68-83, :200, :213."""
+        torch = self.torch
+        if expansion_factor < 1:
+            raise ValueError("Expension factors < 1 not supported.")
+        if getattr(self, "_plane_key", None) != id(plane):
+            self._plane_dev = torch.from_numpy(np.ascontiguousarray(plane, np.float32)).to(self.device)
+            self._plane_key = id(plane)
+        n = plane.shape[0]
+        side = int(n * tile_relative_size * expansion_factor)
+        pad = int(n * tile_relative_size * (expansion_factor - 1) / 2)
+        org = np.array([[int(n * sh[0]) - pad, int(n * sh[1]) - pad] for sh in shifts], np.int32).reshape(-1, 2)
+        out = torch.empty((len(org), n_pixel_tile, n_pixel_tile), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        per_call = max(1, int(2 ** 30 // (8 * side * side)))           # float64 workspace <= 1 GiB
+        for i0 in range(0, len(org), per_call):
+            o = torch.from_numpy(org[i0:i0 + per_call]).to(self.device)
+            self._lib.zoom_tiles(self._plane_dev.device.index or 0, self._plane_dev.data_ptr(), plane.shape[0], plane.shape[1],
+                                 o.data_ptr(), side, o.shape[0], n_pixel_tile, mode, out[i0:i0 + per_call].data_ptr(), stream)
+            torch.cuda.current_stream(self.device).synchronize()       # `o` may be freed after return
+        return out
+
     def paint(self, painter, tiles, z, batch):
-        """(n, T, T) host tiles -> painted tiles as a device tensor."""
+        """(n, T, T) tiles (host array or device tensor) -> painted tiles as a device tensor."""
         torch = self.torch
         n = tiles.shape[0]
+        on_device = isinstance(tiles, torch.Tensor)
         out = torch.empty((n, *tiles.shape[1:]), dtype=torch.float32, device=self.device)
+        if on_device and not hasattr(painter, "paint_batch_device"):
+            tiles, on_device = tiles.cpu().numpy(), False
         if hasattr(painter, "paint_batch_device"):
             for i0 in range(0, n, batch):
                 sl = slice(i0, min(n, i0 + batch))
-                painter.paint_batch_device(torch.from_numpy(np.ascontiguousarray(tiles[sl], np.float32)).to(self.device),
-                                           z=z, out=out[sl])
+                chunk = tiles[sl].contiguous() if on_device else \
+                    torch.from_numpy(np.ascontiguousarray(tiles[sl], np.float32)).to(self.device)
+                painter.paint_batch_device(chunk, z=z, out=out[sl])
         elif hasattr(painter, "paint_batch"):
             for i0 in range(0, n, batch):
                 sl = slice(i0, min(n, i0 + batch))
@@ -221,13 +249,17 @@ def process_SLICS(painter,
                     say(f"  Loading {fn}.")
                     shift = shifts[i]
                 say("  Extracting tile.")
-                tile = get_tile(plane, shift=shift, tile_relative_size=delta_size[i] / MASSPLANE_SIZE,
-                                expansion_factor=tile_size / delta_size[i])
-                if SLICS_density:
-                    tile = tile - tile.min()
-                tile = _zoom(tile, n_pixel_tile, "mirror")
+                if hasattr(be, "extract_tiles") and not SLICS_density:
+                    tile = be.extract_tiles(plane, [shift], delta_size[i] / MASSPLANE_SIZE, n_pixel_tile, "mirror",
+                                            expansion_factor=tile_size / delta_size[i])
+                else:
+                    tile = get_tile(plane, shift=shift, tile_relative_size=delta_size[i] / MASSPLANE_SIZE,
+                                    expansion_factor=tile_size / delta_size[i])
+                    if SLICS_density:
+                        tile = tile - tile.min()
+                    tile = _zoom(tile, n_pixel_tile, "mirror")[None]
                 say("  Painting on tile.")
-                painted = be.to_host(be.paint(painter, tile[None], z_slice[i], batch))[0]
+                painted = be.to_host(be.paint(painter, tile, z_slice[i], batch))[0]
                 c = (1 - delta_size[i] / tile_size) / 2
                 painted = get_tile(painted, shift=(c, c), tile_relative_size=delta_size[i] / tile_size)
             results.append(("mass", painted))
@@ -240,19 +272,27 @@ def process_SLICS(painter,
         origins, slices = generate_tiling(n_pixel_plane=n_pixel_plane, n_pixel_tile=n_pixel_tile, min_tile_overlap=0.5)
         say(f"  Using {len(origins)} tiles (on each side)")
         planes = be.new_planes(n_pixel_plane)
-        tiles, dest = [], []
+        on_device = hasattr(be, "extract_tiles")      # crop + cubic-spline zoom on the GPU
+        tiles, shifts, dest = [], [], []
         for j, xs in enumerate(origins):
             for k, ys in enumerate(origins):
                 mine = (item % world_size) == rank
                 item += 1
                 if not mine:
                     continue
-                tile = get_tile(delta, shift=(xs, ys), tile_relative_size=tile_size / delta_size[i])
-                tiles.append(_zoom(tile, n_pixel_tile, "reflect"))
+                if on_device:
+                    shifts.append((xs, ys))
+                else:
+                    tile = get_tile(delta, shift=(xs, ys), tile_relative_size=tile_size / delta_size[i])
+                    tiles.append(_zoom(tile, n_pixel_tile, "reflect"))
                 dest.append((slices[j][k][0].start, slices[j][k][1].start))
                 say(f"    Painting on tile {j + 1}-{k + 1}")
-        if tiles:
-            painted = be.paint(painter, np.stack(tiles).astype(np.float32, copy=False), z_slice[i], batch)
+        if dest:
+            if on_device:
+                tiles = be.extract_tiles(delta, shifts, tile_size / delta_size[i], n_pixel_tile, "reflect")
+            else:
+                tiles = np.stack(tiles).astype(np.float32, copy=False)
+            painted = be.paint(painter, tiles, z_slice[i], batch)
             be.accumulate(planes, painted, dest, 0.05, 0.5)
         results.append(("delta", planes))
 

@@ -155,6 +155,14 @@ int bp_stitch_accumulate(double* plane_num, double* plane_den, int n_pixel_plane
 int bp_stitch_finalize(const double* plane_num, const double* plane_den, double* plane,
                        size_t n_pixels, void* stream);
 
+/* ---- lightcone tile extraction (reference process_SLICS.py:68-83 get_tile + :200/:213 scipy.ndimage.zoom) ---- */
+enum { BP_ZOOM_REFLECT = 0, BP_ZOOM_MIRROR = 1 };   /* scipy boundary modes "reflect" / "mirror" */
+/* n tiles: periodic side x side crop of the float32 plane (plane_h x plane_w) at origins[t] = (row0, col0), then
+ * cubic-spline resampling (order 3, prefilter, grid_mode off -- scipy.ndimage.zoom defaults) to out_side x out_side.
+ * plane, origins (int32 [n][2]) and out (float32 [n][out_side][out_side]) are device pointers on `device`. */
+int bp_zoom_tiles(int device, const float* plane, int plane_h, int plane_w, const int32_t* origins, int side, int n,
+                  int out_side, int mode, float* out, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 /* copy the activation after layer `layer` of sub-network `stack` (0 prior, 1 p_z_in, 2 p_y_z_in,
  * 3 p_mu_out; CGAN: 0) of the last paint call to host as float32 [n][C][H][W]; needs

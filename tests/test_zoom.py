@@ -1,0 +1,53 @@
+"""Tile extraction / cubic-spline zoom: the numpy restatement is pinned against scipy
+(CPU), the CUDA kernels against scipy on the GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _field(n, seed):
+    import scipy.ndimage
+    g = scipy.ndimage.gaussian_filter(np.random.default_rng(seed).standard_normal((n, n)), 2.0, mode="wrap")
+    return np.exp(g / g.std() - 0.5).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["reflect", "mirror"])
+@pytest.mark.parametrize("side,out", [(37, 64), (100, 64), (64, 64), (5, 16)])
+def test_zoom_oracle_matches_scipy(mode, side, out):
+    import scipy.ndimage
+    from oracle import zoom_oracle
+    tile = _field(side, side)
+    ref = scipy.ndimage.zoom(tile, zoom=out / side, mode=mode)
+    assert ref.shape == (out, out)
+    got = zoom_oracle.zoom(tile, out, mode)
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["reflect", "mirror"])
+def test_gpu_zoom_tiles_match_scipy(mode):
+    import scipy.ndimage
+    import torch
+    from baryon_painter_b200 import _lib
+    from baryon_painter_b200 import process_SLICS as ps
+    plane = _field(300, 3)
+    dev = torch.device("cuda:0")
+    d_plane = torch.from_numpy(plane).to(dev)
+    rel = 0.37
+    shifts = [(0.0, 0.0), (0.9, 0.15), (0.5, 0.95)]                 # the last two wrap around the plane edge
+    side = int(plane.shape[0] * rel)
+    org = torch.tensor([[int(plane.shape[0] * a), int(plane.shape[1] * b)] for a, b in shifts], dtype=torch.int32, device=dev)
+    out = torch.empty((len(shifts), 128, 128), dtype=torch.float32, device=dev)
+    _lib.zoom_tiles(0, d_plane.data_ptr(), plane.shape[0], plane.shape[1], org.data_ptr(), side, len(shifts), 128, mode,
+                    out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    got = out.cpu().numpy()
+    for t, sh in enumerate(shifts):
+        tile = ps.get_tile(plane, shift=sh, tile_relative_size=rel)
+        ref = scipy.ndimage.zoom(tile, zoom=128 / tile.shape[0], mode=mode)
+        # float64 spline arithmetic on both sides, float32 result: a few ulp
+        np.testing.assert_allclose(got[t], ref, rtol=3e-6, atol=3e-6)
