@@ -377,14 +377,21 @@ struct V2Ref { int stack, index; Layer* l; bool w; int need_b; };
 // device time of one launch of a built layer over a full chunk (median of three after a warm-up launch)
 static int g_tune_launches = 0;
 static std::string g_tune_choices;
-static int v2_forced_choice(int stack, int index) {
+static int v2_forced_choice(int stack, int index) {      // "stack.index=candidate[:tiling]" -> candidate + 1000 * tiling
   const char* e = getenv("BP_V2_CHOICES");
   if (!e) return -1;
   const std::string key = std::to_string(stack) + "." + std::to_string(index) + "=";
   const std::string sv(e);
   size_t pos = 0;
   while ((pos = sv.find(key, pos)) != std::string::npos) {
-    if (pos == 0 || sv[pos - 1] == ',') return atoi(sv.c_str() + pos + key.size());
+    if (pos == 0 || sv[pos - 1] == ',') {
+      const char* q = sv.c_str() + pos + key.size();
+      const int cand = atoi(q);
+      const char* colon = strchr(q, ':');
+      const char* comma = strchr(q, ',');
+      const int rank = (colon && (!comma || colon < comma)) ? atoi(colon + 1) : 0;
+      return cand + 1000 * rank;
+    }
     ++pos;
   }
   return -1;
@@ -463,35 +470,54 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       if (rc != BP_OK) return rc;
       // several formulations of one layer (pixel packing of the narrow stride-1 convolutions): the issue-cycle
       // model orders them, the device decides -- each one that fits is timed on a full chunk and the fastest kept
-      const int max_tune = getenv("BP_V2_NOTUNE") ? 1 : 20;
+      const bool tune = getenv("BP_V2_NOTUNE") == nullptr;
+      const bool tlog = getenv("BP_V2_TUNE_LOG") != nullptr;
+      const int max_tune = tune ? 20 : 1, max_rank = tune ? 4 : 1;
       float best_ms = 0.f;
-      int built = 0, ci = -1, best_ci = -1;
-      // BP_V2_CHOICES="stack.index=candidate,..." replays an earlier run's selection without timing (profilers
-      // serialise launches and would perturb it); BP_V2_TUNE_LOG prints the string to replay
-      const int forced = v2_forced_choice(r.stack, r.index);
+      int built = 0, ci = -1, best_ci = -1, best_rank = 0;
+      // BP_V2_CHOICES="stack.index=candidate:tiling,..." replays an earlier run's selection without timing
+      // (profilers serialise launches and would perturb it); BP_V2_TUNE_LOG prints the string to replay
+      const int forced = v2_forced_choice(r.stack, r.index);          // candidate + 1000 * tiling rank, or -1
+      const void* skip_ptr = op.skip >= 0 ? P.acts[op.skip].ptr : nullptr;
       rc = BP_E_UNSUPPORTED;
+      // pass 1: every formulation with the tiling the cost model likes best
       for (const WSpec& sp : cands) {
         ++ci;
-        if (forced >= 0 && ci != forced) continue;
+        if (forced >= 0 && ci != forced % 1000) continue;
         if (built >= max_tune) break;
         WLayer* w = nullptr;
-        int rb = wconv_build(sp, P.acts[cur], net->chunk, &w);
+        int rb = wconv_build(sp, P.acts[cur], net->chunk, &w, forced >= 0 ? forced / 1000 : 0);
         if (rb == BP_E_UNSUPPORTED) continue;
         if (rb != BP_OK) { rc = rb; break; }
         ++built;
         rc = BP_OK;
-        if (cands.size() == 1 || max_tune == 1 || forced >= 0) { op.w = w; best_ci = ci; break; }
+        if (!tune || forced >= 0) { op.w = w; best_ci = ci; break; }
         float ms = 0.f;
-        rb = v2_time_layer(w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, net->chunk, &ms);
+        rb = v2_time_layer(w, P.acts[op.out], skip_ptr, net->chunk, &ms);
         if (rb != BP_OK) { wconv_free(w); rc = rb; break; }
-        if (getenv("BP_V2_TUNE_LOG"))
-          fprintf(stderr, "[tune]   %d.%d N=%d G=%d Jy=%d mode=%d: %.3f ms\n", r.stack, r.index, sp.N, sp.G, sp.Jy, sp.mode, ms);
+        if (tlog) fprintf(stderr, "[tune]   %d.%d N=%d G=%d Jy=%d mode=%d: %.3f ms\n", r.stack, r.index, sp.N, sp.G, sp.Jy, sp.mode, ms);
         if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; best_ci = ci; }
         else wconv_free(w);
       }
       if (rc != BP_OK) { if (op.w) wconv_free(op.w); op.w = nullptr; return rc; }
-      if (built > 1 && getenv("BP_V2_TUNE_LOG")) {
-        g_tune_choices += std::to_string(r.stack) + "." + std::to_string(r.index) + "=" + std::to_string(best_ci) + ",";
+      // pass 2: the model's next tilings (strip width, M-tiles per region, stage size, ring depth) of the winner
+      if (tune && forced < 0) {
+        for (int rank = 1; rank < max_rank; ++rank) {
+          WLayer* w = nullptr;
+          int rb = wconv_build(cands[best_ci], P.acts[cur], net->chunk, &w, rank);
+          if (rb == BP_E_UNSUPPORTED) break;
+          if (rb != BP_OK) { wconv_free(op.w); op.w = nullptr; return rb; }
+          float ms = 0.f;
+          rb = v2_time_layer(w, P.acts[op.out], skip_ptr, net->chunk, &ms);
+          if (rb != BP_OK) { wconv_free(w); wconv_free(op.w); op.w = nullptr; return rb; }
+          if (tlog) fprintf(stderr, "[tune]   %d.%d candidate %d tiling %d: %.3f ms (best so far %.3f)\n", r.stack, r.index, best_ci, rank, ms, best_ms);
+          if (ms < best_ms) { wconv_free(op.w); op.w = w; best_ms = ms; best_rank = rank; }
+          else wconv_free(w);
+        }
+      }
+      if (tune && forced < 0 && tlog) {
+        g_tune_choices += std::to_string(r.stack) + "." + std::to_string(r.index) + "=" + std::to_string(best_ci) + ":" +
+                          std::to_string(best_rank) + ",";
         fprintf(stderr, "[tune] %d.%d conv %d->%d k%d: %d formulations timed, best %.3f ms (tune launches so far %d) BP_V2_CHOICES=%s\n",
                 r.stack, r.index, d.cin, d.cout, d.kernel, built, best_ms, g_tune_launches, g_tune_choices.c_str());
       }

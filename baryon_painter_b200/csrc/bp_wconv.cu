@@ -644,7 +644,7 @@ static uint16_t w_to16(float v, int fmt) {
 
 static double w_mma_floor(int N) { return std::max(45.5, std::max((4096.0 + 32.0 * N) / 128.0, N / 2.0)); }
 
-int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
+int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out, int rank) {
   *out = nullptr;
   BP_REQUIRE(!in.f32 && in.ptr, BP_E_INVALID, "window GEMM input must be a 16-bit NHWC tensor");
   const int Cs = in.b * in.b * in.Cp;                 // stored channels per stored pixel
@@ -719,6 +719,7 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
   for (const Grid& g : grids) ntl_max = std::max(ntl_max, g.ntl);
   struct Choice { double score; int Wt, T_r, gl, nbst; };
   Choice best{1e30, 0, 0, 0, 0};
+  std::vector<Choice> all;
   std::vector<int> wts;
   if (sp.mode == W_LINE) {
     wts.push_back(std::min(sp.OWl, 128));
@@ -755,9 +756,27 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out) {
           const double buffered = (double)nbst * mma_stage * fl;
           if (buffered < 2500.0) cyc *= 1.0 + 0.15 * (2500.0 - buffered) / 2500.0;
           cyc += 400.0 / (T_r * max_taps * nkb * kpu);          // per-region handshakes
-          if (cyc < best.score) best = Choice{cyc, Wt, T_r, gl, nbst};
+          all.push_back(Choice{cyc, Wt, T_r, gl, nbst});
         }
       }
+    }
+  }
+  // `rank` walks down the model's ordering (0 = its best): the net builder times the first few and keeps the
+  // fastest, because the model is only good to ~20 % (it mis-ranks ring depth against stage size in particular).
+  // Deeper rings of the same (Wt, T_r, gl) only count once.
+  std::sort(all.begin(), all.end(), [](const Choice& x, const Choice& y) { return x.score < y.score; });
+  {
+    std::vector<Choice> uniq;
+    for (const Choice& c : all) {
+      bool seen = false;
+      for (const Choice& u : uniq) seen = seen || (u.Wt == c.Wt && u.T_r == c.T_r && u.gl == c.gl);
+      if (!seen) uniq.push_back(c);
+    }
+    if (rank < (int)uniq.size()) best = uniq[rank];
+    else if (!uniq.empty() && rank > 0) {
+      delete wl;
+      set_error("window GEMM: only %d tilings fit", (int)uniq.size());
+      return BP_E_UNSUPPORTED;
     }
   }
   if (best.Wt == 0) {

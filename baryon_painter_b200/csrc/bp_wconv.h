@@ -60,7 +60,8 @@ struct WLayer;   // opaque (bp_wconv.cu)
 
 // builds the packed weights / k-step tables / TMA tensor map for `spec` reading from `in`
 // (whose device pointer must already be final) with capacity for `nb_max` samples
-int wconv_build(const WSpec& spec, const ActDesc& in, int nb_max, WLayer** out);
+// rank: 0 = the tiling the cost model likes best, 1 = its second choice, ... (BP_E_UNSUPPORTED past the last)
+int wconv_build(const WSpec& spec, const ActDesc& in, int nb_max, WLayer** out, int rank = 0);
 void wconv_free(WLayer* w);
 int wconv_launch(const WLayer* w, const ActDesc& out, const void* skip, int nb, cudaStream_t s);
 int wconv_mma_count(const WLayer* w, int nb, double* cycles_floor);
