@@ -14,4 +14,11 @@ tail -1 gpurun_out/ncu_launch.log | cut -c1-200
 # full capture: the 20 window-GEMM launches of the fourth (timed) device step
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:wconv_kernel -s 60 -c 20 -o gpurun_out/prof_wconv_r01 $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
-ls -la gpurun_out/*.ncu-rep
+# the report (and its source page) is too large to travel back (64 MiB limit): export what profiles/ keeps
+ncu -i gpurun_out/prof_wconv_r01.ncu-rep --page raw --csv > gpurun_out/wconv_raw_r01.csv 2>/dev/null
+( cd /tmp && ncu -i $OLDPWD/gpurun_out/prof_wconv_r01.ncu-rep --page source --csv --print-source sass > /tmp/wconv_source_r01.csv 2>/dev/null )
+for k in 3 4 7 8 17 18; do    # L0, L1, residual conv (open / close), T14, conv7
+  python tools/ncu_stalls.py /tmp/wconv_source_r01.csv 40 $k > gpurun_out/wconv_stalls_r01_k$k.txt 2>&1
+done
+rm -f gpurun_out/prof_wconv_r01.ncu-rep
+du -sh gpurun_out
