@@ -234,17 +234,21 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
   const int nbst = a.nbst, nblk = a.nblk, glines = a.glines, run = a.run;
   const int total_regions = a.total_regions;
   uint32_t pst = 0, ppar = 0, bst = 0, bpar = 0, as = 0, apar = 0;
-  bool pre_ok = false;       // the current weight stage's barrier was already seen complete by an early probe
+  // barriers already seen complete by an early probe: the current weight stage's, the current patch block's,
+  // the current region's accumulator release
+  bool pre_ok = false, pre_p = false, pre_t = false;
   for (int reg = blockIdx.x; reg < total_regions; reg += gridDim.x) {
     const WRegion R = w_decode(a, reg);
     const WPhase P = a.phase[R.pi];
-    W_TWAIT(0, mbar_wait(&tempty[as], apar ^ 1u));
+    if (!pre_t) W_TWAIT(0, mbar_wait(&tempty[as], apar ^ 1u));
+    pre_t = false;
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + as * (uint32_t)(T_R * N);
     const uint32_t row0 = ((uint32_t)((a.top + P.dl0) * a.PW + (a.left + P.du0)) + (uint32_t)R.tile0) * ub16;
     uint32_t acc = 0;
     for (int blk = 0; blk < nblk; ++blk) {
-      W_TWAIT(1, mbar_wait(&full_p[pst], ppar));
+      if (!pre_p) W_TWAIT(1, mbar_wait(&full_p[pst], ppar));
+      pre_p = false;
       tc_fence_after();
       const uint32_t da_blk = a_lo0 + pst * pstage16 + row0;
       int s0 = 0;
@@ -271,6 +275,10 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
         {
           const uint32_t nb_ = bst + 1u == (uint32_t)nbst ? 0u : bst + 1u;
           pre_ok = mbar_test(&full_b[nb_], nb_ == 0u ? bpar ^ 1u : bpar);
+          if (l0 + glines >= P.ntl) {            // last stage of this K block: the next block's patch, and after
+            pre_p = mbar_test(&full_p[pst ^ 1u], pst == 1u ? ppar ^ 1u : ppar);      // the last block the next
+            if (blk + 1 == nblk) pre_t = mbar_test(&tempty[as ^ 1u], (as == 1u ? apar ^ 1u : apar) ^ 1u);   // accumulator
+          }
         }
 #pragma unroll 2
         for (int sl = ns1; sl < ns; ++sl) {
