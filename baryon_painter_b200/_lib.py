@@ -27,7 +27,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 # every symbol declared in include/baryon_painter_b200.h (checked by tests/test_cabi.py)
 EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destroy", "bp_cvae_paint",
            "bp_cvae_paint_host", "bp_cvae_read_prior", "bp_cgan_paint", "bp_cgan_paint_host",
-           "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles",
+           "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles", "bp_zoom_accumulate",
            "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
            "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile", "bp_net_chunk",
            "bp_last_error", "bp_version")
@@ -92,6 +92,7 @@ def load():
     lib.bp_stitch_accumulate.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, f32, vp]
     lib.bp_stitch_finalize.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
     lib.bp_zoom_tiles.argtypes = [i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp]
+    lib.bp_zoom_accumulate.argtypes = [i32, vp, i32, i32, i32, i32, ctypes.c_double, vp, vp]
     lib.bp_net_set_debug.argtypes = [vp, i32]
     lib.bp_net_read_activation.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
     lib.bp_net_set_profile.argtypes = [vp, i32]
@@ -298,6 +299,13 @@ def zoom_tiles(device, plane_ptr, plane_h, plane_w, origins_ptr, side, n, out_si
     side x side crop), float32 out [n,out_side,out_side] = scipy.ndimage.zoom(crop, out_side/side, mode=mode)."""
     check(load().bp_zoom_tiles(int(device), plane_ptr, int(plane_h), int(plane_w), origins_ptr, int(side), int(n),
                                int(out_side), ZOOM_MODES[mode], out_ptr, stream))
+
+
+def zoom_accumulate(device, plane_ptr, side, out_side, order, mode, scale, map_ptr, stream=0):
+    """Device pointers: float64 plane [side, side], float64 map [out_side, out_side];
+    map += scale * scipy.ndimage.zoom(nan_to_zero(plane), out_side / side, order=order, mode=mode)."""
+    check(load().bp_zoom_accumulate(int(device), plane_ptr, int(side), int(out_side), int(order), ZOOM_MODES[mode],
+                                    float(scale), map_ptr, stream))
 
 
 def pinned_empty(shape, dtype=np.float32):

@@ -4,6 +4,8 @@
 //     zoom=n_pixel_tile / side, mode="reflect" | "mirror"), i.e. order 3, prefilter on, grid_mode off).
 // The reference runs both on one host core per tile; here a batch of tiles is cropped, prefiltered and resampled
 // by three small kernels and stays on the device for the painter.
+// The same kernels, with the quintic spline (two poles, six taps), project the painted planes onto the Compton-y
+// map (row f2): y_map += scale * zoom(plane, order=5, mode="mirror")  (reference process_SLICS.py:12-66).
 //
 // scipy's algorithm, restated (scipy/ndimage/src/ni_splines.c, ni_interpolation.c; oracle/zoom_oracle.py is the
 // numpy restatement the tests pin against scipy itself):
@@ -26,57 +28,67 @@ namespace bp {
 constexpr double kPole = -0.26794919243112270647;      // sqrt(3) - 2
 
 // ---- crop with wrap-around -> float64 ---------------------------------------------------------------
-__global__ void zoom_crop_kernel(const float* __restrict__ plane, int ph, int pw, const int* __restrict__ origins, int side,
+template <typename T>
+__global__ void zoom_crop_kernel(const T* __restrict__ plane, int ph, int pw, const int* __restrict__ origins, int side,
                                  double* __restrict__ work) {
   const int n = blockIdx.z;
-  const int r0 = origins[2 * n], c0 = origins[2 * n + 1];
+  const int r0 = origins ? origins[2 * n] : 0, c0 = origins ? origins[2 * n + 1] : 0;
   const int y = blockIdx.y;
   int yy = (r0 + y) % ph;
   if (yy < 0) yy += ph;
   for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < side; x += gridDim.x * blockDim.x) {
     int xx = (c0 + x) % pw;
     if (xx < 0) xx += pw;
-    work[((size_t)n * side + y) * side + x] = (double)plane[(size_t)yy * pw + xx];
+    const double v = (double)plane[(size_t)yy * pw + xx];
+    // float64 planes are the painted planes on their way into the y-map: NaN -> 0 as create_y_map does (:54)
+    work[((size_t)n * side + y) * side + x] = (sizeof(T) == 8 && v != v) ? 0.0 : v;
   }
 }
 
 // ---- spline prefilter along one axis: one thread per line ------------------------------------------------
 // element i of line l of tile n: work[n*side*side + l*line_stride + i*elem_stride]
 __global__ void zoom_filter_kernel(double* __restrict__ work, int side, int ntiles, long long line_stride, long long elem_stride,
-                                   int mirror) {
+                                   int mirror, int npoles, double pole0, double pole1) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)ntiles * side) return;
   const int n = (int)(t / side), l = (int)(t % side);
   double* c = work + (size_t)n * side * side + (size_t)l * line_stride;
   const int len = side;
   if (len < 2) return;
-  const double z = kPole;
 #define C(i) c[(size_t)(i) * elem_stride]
-  for (int i = 0; i < len; ++i) C(i) *= 6.0;               // (1 - z)(1 - 1/z)
-  // causal initialisation
-  if (mirror) {
-    const double z_n_1 = pow(z, (double)(len - 1));
-    double z_i = z, s = C(0) + z_n_1 * C(len - 1);
-    for (int i = 1; i < len - 1; ++i) {
-      s += z_i * (C(i) + z_n_1 * C(len - 1 - i));
-      z_i *= z;
-    }
-    C(0) = s / (1.0 - z_n_1 * z_n_1);
-  } else {
-    const double z_n = pow(z, (double)len);
-    const double c0 = C(0);
-    double z_i = z, s = C(0) + z_n * C(len - 1);
-    for (int i = 1; i < len; ++i) {
-      s += z_i * (C(i) + z_n * C(len - 1 - i));
-      z_i *= z;
-    }
-    C(0) = s * (z / (1.0 - z_n * z_n)) + c0;
+  double gain = 1.0;
+  for (int p = 0; p < npoles; ++p) {
+    const double z = p == 0 ? pole0 : pole1;
+    gain *= (1.0 - z) * (1.0 - 1.0 / z);
   }
-  for (int i = 1; i < len; ++i) C(i) += z * C(i - 1);
-  // anticausal initialisation
-  if (mirror) C(len - 1) = (z * C(len - 2) + C(len - 1)) * z / (z * z - 1.0);
-  else C(len - 1) *= z / (z - 1.0);
-  for (int i = len - 2; i >= 0; --i) C(i) = z * (C(i + 1) - C(i));
+  for (int i = 0; i < len; ++i) C(i) *= gain;
+  for (int p = 0; p < npoles; ++p) {
+    const double z = p == 0 ? pole0 : pole1;
+    // causal initialisation
+    if (mirror) {
+      const double z_n_1 = pow(z, (double)(len - 1));
+      double z_i = z, s = C(0) + z_n_1 * C(len - 1);
+      for (int i = 1; i < len - 1; ++i) {
+        s += z_i * (C(i) + z_n_1 * C(len - 1 - i));
+        z_i *= z;
+      }
+      C(0) = s / (1.0 - z_n_1 * z_n_1);
+    } else {
+      const double z_n = pow(z, (double)len);
+      const double c0 = C(0);
+      double z_i = z, s = C(0) + z_n * C(len - 1);
+      for (int i = 1; i < len; ++i) {
+        s += z_i * (C(i) + z_n * C(len - 1 - i));
+        z_i *= z;
+      }
+      C(0) = s * (z / (1.0 - z_n * z_n)) + c0;
+    }
+    for (int i = 1; i < len; ++i) C(i) += z * C(i - 1);
+    // anticausal initialisation
+    if (mirror) C(len - 1) = (z * C(len - 2) + C(len - 1)) * z / (z * z - 1.0);
+    else C(len - 1) *= z / (z - 1.0);
+    for (int i = len - 2; i >= 0; --i) C(i) = z * (C(i + 1) - C(i));
+  }
 #undef C
 }
 
@@ -101,42 +113,71 @@ __device__ __forceinline__ int zoom_fold(int idx, int len, int mirror) {
   return idx >= len ? s2 - idx - 1 : idx;
 }
 
-__device__ __forceinline__ void zoom_weights(double x, int* start, double w[4]) {
+// B-spline basis weights of the ORDER + 1 coefficients around x (ORDER = 3 or 5), first coefficient index in *start
+template <int ORDER>
+__device__ __forceinline__ void zoom_weights(double x, int* start, double* w) {
   const double f = floor(x);
   const double t = x - f;
-  *start = (int)f - 1;
-  const double t1 = 1.0 - t;
-  w[0] = t1 * t1 * t1 / 6.0;
-  w[1] = (t * t * (t - 2.0) * 3.0 + 4.0) / 6.0;
-  w[2] = (t1 * t1 * (t1 - 2.0) * 3.0 + 4.0) / 6.0;
-  w[3] = t * t * t / 6.0;
+  *start = (int)f - ORDER / 2;
+  if (ORDER == 3) {
+    const double t1 = 1.0 - t;
+    w[0] = t1 * t1 * t1 / 6.0;
+    w[1] = (t * t * (t - 2.0) * 3.0 + 4.0) / 6.0;
+    w[2] = (t1 * t1 * (t1 - 2.0) * 3.0 + 4.0) / 6.0;
+    w[3] = t * t * t / 6.0;
+  } else {
+    // quintic B-spline beta5(y) at the distances y = |t + 2 - k|
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double y = fabs(t + 2.0 - (double)k);
+      double v;
+      if (y < 1.0) {
+        const double y2 = y * y;
+        v = y2 * (y2 * (0.25 - y / 12.0) - 0.5) + 0.55;
+      } else if (y < 2.0) {
+        v = y * (y * (y * (y * (y / 24.0 - 0.375) + 1.25) - 1.75) + 0.625) + 0.425;
+      } else if (y < 3.0) {
+        const double r = 3.0 - y, r2 = r * r;
+        v = r * r2 * r2 / 120.0;
+      } else {
+        v = 0.0;
+      }
+      w[k] = v;
+    }
+  }
 }
 
 // ---- evaluation: one thread per output pixel -----------------------------------------------------------
-__global__ void zoom_eval_kernel(const double* __restrict__ work, int side, int out_side, int mirror, float* __restrict__ out) {
+// ACCUM = false: float32 tiles out[n][oy][ox] = value;  ACCUM = true: float64 map out[oy][ox] += scale * value
+template <int ORDER, bool ACCUM>
+__global__ void zoom_eval_kernel(const double* __restrict__ work, int side, int out_side, int mirror, void* __restrict__ out_,
+                                 double scale_out) {
+  constexpr int T = ORDER + 1;
   const int n = blockIdx.z;
   const int oy = blockIdx.y;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   if (ox >= out_side) return;
   const double scale = out_side > 1 ? (double)(side - 1) / (double)(out_side - 1) : 0.0;
   int sy, sx;
-  double wy[4], wx[4];
-  zoom_weights((double)oy * scale, &sy, wy);
-  zoom_weights((double)ox * scale, &sx, wx);
+  double wy[T], wx[T];
+  zoom_weights<ORDER>((double)oy * scale, &sy, wy);
+  zoom_weights<ORDER>((double)ox * scale, &sx, wx);
   const double* c = work + (size_t)n * side * side;
-  int ix[4];
+  int ix[T];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) ix[b] = zoom_fold(sx + b, side, mirror);
+  for (int b = 0; b < T; ++b) ix[b] = zoom_fold(sx + b, side, mirror);
   double acc = 0.0;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
+  for (int a = 0; a < T; ++a) {
     const double* row = c + (size_t)zoom_fold(sy + a, side, mirror) * side;
     double r = 0.0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) r += wx[b] * row[ix[b]];
+    for (int b = 0; b < T; ++b) r += wx[b] * row[ix[b]];
     acc += wy[a] * r;
   }
-  out[((size_t)n * out_side + oy) * out_side + ox] = (float)acc;
+  const size_t o = ((size_t)n * out_side + oy) * out_side + ox;
+  if (ACCUM) static_cast<double*>(out_)[o] += scale_out * acc;
+  else static_cast<float*>(out_)[o] = (float)acc;
 }
 
 // grow-only float64 workspace per device
@@ -161,6 +202,25 @@ static double* zoom_workspace(int device, size_t elems) {
 
 using namespace bp;
 
+namespace {
+constexpr double kPole5a = -0.43057534709997381;       // sqrt(67.5 - sqrt(4436.25)) + sqrt(26.25) - 6.5
+constexpr double kPole5b = -0.043096288203264652;      // sqrt(67.5 + sqrt(4436.25)) - sqrt(26.25) - 6.5
+
+// prefilter (rows, then columns) of n cropped tiles already in `work`
+int zoom_prefilter(double* work, int side, int n, int order, int mirror, cudaStream_t s) {
+  const long long lines = (long long)n * side;
+  const int fb = 64;
+  const int npoles = order == 3 ? 1 : 2;
+  const double p0 = order == 3 ? kPole : kPole5a, p1 = kPole5b;
+  // scipy filters axis by axis; the recursions along different axes commute
+  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, (long long)side, 1LL, mirror, npoles, p0, p1);
+  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, 1LL, (long long)side, mirror, npoles, p0, p1);
+  launch_counter() += 2;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+}  // namespace
+
 extern "C" int bp_zoom_tiles(int device, const float* plane, int plane_h, int plane_w, const int* origins, int side, int n,
                              int out_side, int mode, float* out, void* stream) {
   BP_REQUIRE(plane && origins && out, BP_E_INVALID, "zoom_tiles: null pointer");
@@ -173,14 +233,33 @@ extern "C" int bp_zoom_tiles(int device, const float* plane, int plane_h, int pl
   double* work = zoom_workspace(device, (size_t)n * side * side);
   BP_REQUIRE(work, BP_E_NOMEM, "zoom_tiles: %zu bytes of workspace", (size_t)n * side * side * sizeof(double));
   const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
-  zoom_crop_kernel<<<dim3((side + 255) / 256, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
-  const long long lines = (long long)n * side;
-  const int fb = 64;
-  // along x (lines = rows), then along y (lines = columns): scipy filters axis by axis and the recursions commute
-  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, (long long)side, 1LL, mirror);
-  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, 1LL, (long long)side, mirror);
-  zoom_eval_kernel<<<dim3((out_side + 127) / 128, out_side, n), 128, 0, s>>>(work, side, out_side, mirror, out);
-  launch_counter() += 4;
+  zoom_crop_kernel<float><<<dim3((side + 255) / 256, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
+  int rc = zoom_prefilter(work, side, n, 3, mirror, s);
+  if (rc != BP_OK) return rc;
+  zoom_eval_kernel<3, false><<<dim3((out_side + 127) / 128, out_side, n), 128, 0, s>>>(work, side, out_side, mirror, out, 1.0);
+  launch_counter() += 2;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+extern "C" int bp_zoom_accumulate(int device, const double* plane, int side, int out_side, int order, int mode, double scale,
+                                  double* map, void* stream) {
+  BP_REQUIRE(plane && map, BP_E_INVALID, "zoom_accumulate: null pointer");
+  BP_REQUIRE(side >= 2 && out_side >= 1, BP_E_INVALID, "zoom_accumulate: bad geometry (side %d, out %d)", side, out_side);
+  BP_REQUIRE(order == 3 || order == 5, BP_E_UNSUPPORTED, "zoom_accumulate: spline order %d (3 and 5 are implemented)", order);
+  BP_REQUIRE(mode == BP_ZOOM_REFLECT || mode == BP_ZOOM_MIRROR, BP_E_UNSUPPORTED, "zoom_accumulate: boundary mode %d", mode);
+  BP_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* work = zoom_workspace(device, (size_t)side * side);
+  BP_REQUIRE(work, BP_E_NOMEM, "zoom_accumulate: %zu bytes of workspace", (size_t)side * side * sizeof(double));
+  const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
+  zoom_crop_kernel<double><<<dim3((side + 255) / 256, side, 1), 256, 0, s>>>(plane, side, side, nullptr, side, work);
+  int rc = zoom_prefilter(work, side, 1, order, mirror, s);
+  if (rc != BP_OK) return rc;
+  const dim3 grid((out_side + 127) / 128, out_side, 1);
+  if (order == 3) zoom_eval_kernel<3, true><<<grid, 128, 0, s>>>(work, side, out_side, mirror, map, scale);
+  else zoom_eval_kernel<5, true><<<grid, 128, 0, s>>>(work, side, out_side, mirror, map, scale);
+  launch_counter() += 2;
   BP_CUDA_TRY(cudaGetLastError());
   return BP_OK;
 }

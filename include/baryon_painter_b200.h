@@ -162,6 +162,11 @@ enum { BP_ZOOM_REFLECT = 0, BP_ZOOM_MIRROR = 1 };   /* scipy boundary modes "ref
  * plane, origins (int32 [n][2]) and out (float32 [n][out_side][out_side]) are device pointers on `device`. */
 int bp_zoom_tiles(int device, const float* plane, int plane_h, int plane_w, const int32_t* origins, int side, int n,
                   int out_side, int mode, float* out, void* stream);
+/* Compton-y projection step (reference process_SLICS.py:12-66, create_y_map loop body):
+ * map[out_side][out_side] += scale * scipy.ndimage.zoom(where(isnan(plane), 0, plane), out_side/side, order, mode)
+ * for one float64 side x side painted plane; order 3 or 5; plane and map are device pointers. */
+int bp_zoom_accumulate(int device, const double* plane, int side, int out_side, int order, int mode, double scale,
+                       double* map, void* stream);
 
 /* ---- introspection ---------------------------------------------------------------------- */
 /* copy the activation after layer `layer` of sub-network `stack` (0 prior, 1 p_z_in, 2 p_y_z_in,

@@ -4,39 +4,43 @@ in scipy: scipy/ndimage/src/ni_splines.c (spline prefilter) and ni_interpolation
 what ``csrc/bp_zoom.cu`` computes and is pinned against scipy itself in tests/test_zoom.py.  Only tests import it."""
 import numpy as np
 
-POLE = np.sqrt(3.0) - 2.0
+POLES = {3: (np.sqrt(3.0) - 2.0,),
+         5: (np.sqrt(67.5 - np.sqrt(4436.25)) + np.sqrt(26.25) - 6.5, np.sqrt(67.5 + np.sqrt(4436.25)) - np.sqrt(26.25) - 6.5)}
 
 
-def _filter_line(c, mirror):
-    """In-place cubic B-spline prefilter of one float64 line (ni_splines.c: apply_filter, _init_causal_*, _init_anticausal_*)."""
+def _filter_line(c, mirror, poles):
+    """In-place B-spline prefilter of one float64 line (ni_splines.c: apply_filter, _init_causal_*, _init_anticausal_*)."""
     n = len(c)
     if n < 2:
         return
-    z = POLE
-    c *= (1 - z) * (1 - 1 / z)
-    if mirror:
-        z_n_1 = z ** (n - 1)
-        z_i, s = z, c[0] + z_n_1 * c[n - 1]
-        for i in range(1, n - 1):
-            s += z_i * (c[i] + z_n_1 * c[n - 1 - i])
-            z_i *= z
-        c[0] = s / (1 - z_n_1 * z_n_1)
-    else:
-        z_n = z ** n
-        c0 = c[0]
-        z_i, s = z, c[0] + z_n * c[n - 1]
+    gain = 1.0
+    for z in poles:
+        gain *= (1 - z) * (1 - 1 / z)
+    c *= gain
+    for z in poles:
+        if mirror:
+            z_n_1 = z ** (n - 1)
+            z_i, s = z, c[0] + z_n_1 * c[n - 1]
+            for i in range(1, n - 1):
+                s += z_i * (c[i] + z_n_1 * c[n - 1 - i])
+                z_i *= z
+            c[0] = s / (1 - z_n_1 * z_n_1)
+        else:
+            z_n = z ** n
+            c0 = c[0]
+            z_i, s = z, c[0] + z_n * c[n - 1]
+            for i in range(1, n):
+                s += z_i * (c[i] + z_n * c[n - 1 - i])
+                z_i *= z
+            c[0] = s * (z / (1 - z_n * z_n)) + c0
         for i in range(1, n):
-            s += z_i * (c[i] + z_n * c[n - 1 - i])
-            z_i *= z
-        c[0] = s * (z / (1 - z_n * z_n)) + c0
-    for i in range(1, n):
-        c[i] += z * c[i - 1]
-    if mirror:
-        c[n - 1] = (z * c[n - 2] + c[n - 1]) * z / (z * z - 1)
-    else:
-        c[n - 1] *= z / (z - 1)
-    for i in range(n - 2, -1, -1):
-        c[i] = z * (c[i + 1] - c[i])
+            c[i] += z * c[i - 1]
+        if mirror:
+            c[n - 1] = (z * c[n - 2] + c[n - 1]) * z / (z * z - 1)
+        else:
+            c[n - 1] *= z / (z - 1)
+        for i in range(n - 2, -1, -1):
+            c[i] = z * (c[i + 1] - c[i])
 
 
 def _fold(idx, n, mirror):
@@ -61,29 +65,42 @@ def _fold(idx, n, mirror):
     return s2 - idx - 1 if idx >= n else idx
 
 
-def _weights(x):
+def _beta5(y):
+    y = abs(y)
+    if y < 1:
+        return y * y * (y * y * (0.25 - y / 12) - 0.5) + 0.55
+    if y < 2:
+        return y * (y * (y * (y * (y / 24 - 0.375) + 1.25) - 1.75) + 0.625) + 0.425
+    if y < 3:
+        return (3 - y) ** 5 / 120
+    return 0.0
+
+
+def _weights(x, order):
     f = np.floor(x)
     t = x - f
-    t1 = 1 - t
-    return int(f) - 1, np.array([t1 ** 3 / 6, (t * t * (t - 2) * 3 + 4) / 6, (t1 * t1 * (t1 - 2) * 3 + 4) / 6, t ** 3 / 6])
+    if order == 3:
+        t1 = 1 - t
+        return int(f) - 1, np.array([t1 ** 3 / 6, (t * t * (t - 2) * 3 + 4) / 6, (t1 * t1 * (t1 - 2) * 3 + 4) / 6, t ** 3 / 6])
+    return int(f) - 2, np.array([_beta5(t + 2 - k) for k in range(6)])
 
 
-def zoom(tile, out_side, mode):
-    """scipy.ndimage.zoom(tile, out_side / tile.shape[0], mode=mode) for a square float tile."""
+def zoom(tile, out_side, mode, order=3):
+    """scipy.ndimage.zoom(tile, out_side / tile.shape[0], order=order, mode=mode) for a square float tile."""
     mirror = {"reflect": False, "mirror": True}[mode]
     c = np.array(tile, np.float64)
     n = c.shape[0]
     for r in range(n):
-        _filter_line(c[r], mirror)
+        _filter_line(c[r], mirror, POLES[order])
     for q in range(n):
         col = c[:, q].copy()
-        _filter_line(col, mirror)
+        _filter_line(col, mirror, POLES[order])
         c[:, q] = col
     scale = (n - 1) / (out_side - 1) if out_side > 1 else 0.0
     idx, wts = [], []
     for o in range(out_side):
-        s, w = _weights(o * scale)
-        idx.append([_fold(s + k, n, mirror) for k in range(4)])
+        s, w = _weights(o * scale, order)
+        idx.append([_fold(s + k, n, mirror) for k in range(order + 1)])
         wts.append(w)
     idx, wts = np.array(idx), np.array(wts)
     rows = np.einsum("ok,okx->ox", wts, c[idx])                # (out, n): interpolate along y

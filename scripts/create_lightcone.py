@@ -159,12 +159,13 @@ if __name__ == "__main__":
     if rank == 0:
         output_resolution = int(args.output_resolution)
         create_y_map = baryon_painter_b200.process_SLICS.create_y_map
+        be = baryon_painter_b200.process_SLICS.DeviceBackend(device)       # quintic zoom + sum on the GPU
         y_map = create_y_map(painted_planes, z_SLICS[:n_z], resolution=output_resolution, map_size=10.0,
-                             cosmo=cosmo_SLICS, order=5)
+                             cosmo=cosmo_SLICS, order=5, backend=be)
         np.save(output_file, y_map)
         if n_drop is not None:
             y_map = create_y_map(painted_planes[n_drop:], z_SLICS[n_drop:n_z], resolution=output_resolution,
-                                 map_size=10.0, cosmo=cosmo_SLICS, order=5)
+                                 map_size=10.0, cosmo=cosmo_SLICS, order=5, backend=be)
             np.save(output_file_drop, y_map)
         if args.output_file_planes is not None:
             import pickle

@@ -78,3 +78,8 @@ def test_tile_loop_vs_oracle(precision, tol):
     yd = ps.create_y_map(dev, [0.21, 0.52], 64, 10.0, cosmo, verbose=False)
     yr = ps.create_y_map(ref, [0.21, 0.52], 64, 10.0, cosmo, verbose=False)
     assert rel_l2(yd, yr) <= tol
+    # the same projection on the device (quintic spline, as scripts/create_lightcone.py asks for) against host scipy
+    for order in (3, 5):
+        y_host = ps.create_y_map(dev, [0.21, 0.52], 64, 10.0, cosmo, order=order, verbose=False)
+        y_dev = ps.create_y_map(dev, [0.21, 0.52], 64, 10.0, cosmo, order=order, verbose=False, backend=ps.DeviceBackend("cuda:0"))
+        assert rel_l2(y_dev, y_host) <= 1e-10

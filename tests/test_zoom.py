@@ -28,6 +28,38 @@ def test_zoom_oracle_matches_scipy(mode, side, out):
     np.testing.assert_allclose(got, ref, rtol=2e-6, atol=2e-6)
 
 
+@pytest.mark.parametrize("side,out", [(40, 29), (23, 64)])
+def test_zoom_oracle_order5_matches_scipy(side, out):
+    """create_y_map's call: float64 plane, order 5, mode mirror (reference process_SLICS.py:63)."""
+    import scipy.ndimage
+    from oracle import zoom_oracle
+    plane = _field(side, 7).astype(np.float64)
+    ref = scipy.ndimage.zoom(plane, zoom=out / side, order=5, mode="mirror")
+    assert ref.shape == (out, out)
+    np.testing.assert_allclose(zoom_oracle.zoom(plane, out, "mirror", order=5), ref, rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [3, 5])
+def test_gpu_zoom_accumulate_matches_scipy(order):
+    import scipy.ndimage
+    import torch
+    from baryon_painter_b200 import _lib
+    dev = torch.device("cuda:0")
+    y_ref = np.zeros((96, 96))
+    y_dev = torch.zeros((96, 96), dtype=torch.float64, device=dev)
+    for k, side in enumerate((61, 150)):
+        plane = _field(side, 10 + k).astype(np.float64)
+        plane[3, 5] = np.nan                                   # create_y_map zeroes NaNs first
+        scale = 0.5 + k
+        y_ref += scale * scipy.ndimage.zoom(np.where(np.isnan(plane), 0.0, plane), zoom=96 / side, order=order, mode="mirror")
+        d = torch.from_numpy(plane).to(dev)
+        _lib.zoom_accumulate(0, d.data_ptr(), side, 96, order, "mirror", scale, y_dev.data_ptr(),
+                             torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize()
+    np.testing.assert_allclose(y_dev.cpu().numpy(), y_ref, rtol=1e-10, atol=1e-12)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["reflect", "mirror"])
 def test_gpu_zoom_tiles_match_scipy(mode):
