@@ -51,3 +51,22 @@ def test_cgan_fiducial_shape_runs():
     a = p.paint_batch(tiles, z=[0.0, 1.0])
     b = p.paint_batch(tiles, z=[0.0, 1.0])
     assert a.shape == (2, 512, 512) and np.all(np.isfinite(a)) and np.array_equal(a, b)
+
+
+def test_cgan_host_pipeline_and_out_buffer():
+    """CGAN host path: pipelined chunks, caller-supplied (page-locked) result buffer, sigma(z) per distinct redshift --
+    same numbers whichever way the batch is cut."""
+    import baryon_painter_b200 as bp
+    from baryon_painter_b200 import synthetic
+    from baryon_painter_b200.painter import CGANPainter
+    tile, n = 64, 37
+    g = CGANPainter.synthetic(tile_size=tile, device="cuda:0", precision="fp16", max_batch=64, n_res_blocks=2)
+    tiles = synthetic.synthetic_dm_tiles(8, tile, seed0=3)
+    tiles = np.ascontiguousarray(np.concatenate([tiles] * 5)[:n])
+    zs = np.array([0.0, 0.5, 1.0])[np.arange(n) % 3]
+    ref = g.paint_batch(tiles, z=zs)
+    out = bp.pinned_empty(tiles.shape)
+    got = g.paint_batch(tiles, z=zs, out=out)
+    assert got is out and np.array_equal(out, ref)
+    one = np.stack([g.paint(tiles[i], z=float(zs[i])) for i in (0, 5, 36)])
+    assert np.array_equal(one, ref[[0, 5, 36]])
