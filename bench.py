@@ -125,6 +125,15 @@ def cpu_baseline(n_tiles, threads, warmup=1):
     return n_tiles / dt, dt
 
 
+def workload_config(n, world):
+    """The `config` object of both arms: BASELINE.json configs[1] at `n` tiles per GPU."""
+    return {"workload": "fiducial CVAE batched paint, %d synthetic 512x512 tiles per GPU, fixed eps "
+                        "latents, z=0 (BASELINE.json configs[1])" % n,
+            "weights": "seeded synthetic state_dict, fiducial architecture (trained blob absent)",
+            "l2": "inputs+outputs per step %.0f MB > 126 MB L2" % (2 * n * TILE * TILE * 4 / 1e6),
+            "parallelism": "tiles sharded over %d GPU(s), no collective" % world}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -144,8 +153,7 @@ def run_reference(args):
         "impl": "reference", "metric": "tiles/sec painted (fiducial CVAE)", "value": v, "unit": "tiles/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fiducial CVAE batched paint, %d synthetic 512x512 tiles, fixed latents, z=0"
-                               % args.tiles},
+        "config": workload_config(args.tiles, max(1, args.gpus)),
         "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
                          "sample": "%d batch-1 paint() calls per step (oracle port of the reference torch-CPU "
                                    "path, bit-identical to it in the build container)" % sample},
@@ -302,11 +310,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}.get(args.precision, args.precision), "data": "synthetic",
-            "config": {"workload": "fiducial CVAE batched paint, %d synthetic 512x512 tiles per GPU, fixed eps "
-                                   "latents, z=0 (BASELINE.json configs[1])" % n,
-                       "weights": "seeded synthetic state_dict, fiducial architecture (trained blob absent)",
-                       "l2": "inputs+outputs per step %.0f MB > 126 MB L2" % (2 * n * TILE * TILE * 4 / 1e6),
-                       "parallelism": "tiles sharded over %d GPU(s), no collective" % world},
+            "config": workload_config(n, world),
             "e2e": {"value": total_tiles / (e2e_ms * 1e-3), "unit": "tiles/s",
                     "h2d_bytes_per_step": int(tiles_h.nbytes + eps_h.nbytes), "d2h_bytes_per_step": int(out_h.nbytes)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
