@@ -27,7 +27,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 # every symbol declared in include/baryon_painter_b200.h (checked by tests/test_cabi.py)
 EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destroy", "bp_cvae_paint",
            "bp_cvae_paint_host", "bp_cvae_read_prior", "bp_cgan_paint", "bp_cgan_paint_host",
-           "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles", "bp_zoom_accumulate",
+           "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles", "bp_zoom_accumulate", "bp_plane_prepare",
            "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
            "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile", "bp_net_chunk",
            "bp_last_error", "bp_version")
@@ -93,6 +93,7 @@ def load():
     lib.bp_stitch_finalize.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
     lib.bp_zoom_tiles.argtypes = [i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp]
     lib.bp_zoom_accumulate.argtypes = [i32, vp, i32, i32, i32, i32, ctypes.c_double, vp, vp]
+    lib.bp_plane_prepare.argtypes = [i32, vp, i32, i32, f32, f32, vp, vp]
     lib.bp_net_set_debug.argtypes = [vp, i32]
     lib.bp_net_read_activation.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
     lib.bp_net_set_profile.argtypes = [vp, i32]
@@ -306,6 +307,12 @@ def zoom_accumulate(device, plane_ptr, side, out_side, order, mode, scale, map_p
     map += scale * scipy.ndimage.zoom(nan_to_zero(plane), out_side / side, order=order, mode=mode)."""
     check(load().bp_zoom_accumulate(int(device), plane_ptr, int(side), int(out_side), int(order), ZOOM_MODES[mode],
                                     float(scale), map_ptr, stream))
+
+
+def plane_prepare(device, raw_ptr, rows, cols, add, mul, out_ptr, stream=0):
+    """Device pointers: raw float32 [rows, cols] -> out float32 [cols, rows] = (raw.T + add) * mul (float32 roundings
+    of numpy's in-place ``+=`` / ``*=``)."""
+    check(load().bp_plane_prepare(int(device), raw_ptr, int(rows), int(cols), float(add), float(mul), out_ptr, stream))
 
 
 def pinned_empty(shape, dtype=np.float32):

@@ -180,6 +180,24 @@ __global__ void zoom_eval_kernel(const double* __restrict__ work, int side, int 
   else static_cast<float*>(out_)[o] = (float)acc;
 }
 
+// ---- plane preprocessing: transpose + affine of the raw file contents (row f3) -----------------------------
+// out[c][r] = (raw[r][c] + add) * mul, two separately rounded fp32 operations exactly as numpy's `+=` / `*=`
+// (reference process_SLICS.py:157-159 mass planes, :187-189 delta planes); 32 x 32 tiles through shared memory
+__global__ void plane_prepare_kernel(const float* __restrict__ raw, int rows, int cols, float add, float mul,
+                                     float* __restrict__ out) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) t[j][threadIdx.x] = __fmul_rn(__fadd_rn(raw[(size_t)r * cols + c], add), mul);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = t[threadIdx.x][j];
+  }
+}
+
 // grow-only float64 workspace per device
 static double* zoom_workspace(int device, size_t elems) {
   static std::mutex mu;
@@ -260,6 +278,19 @@ extern "C" int bp_zoom_accumulate(int device, const double* plane, int side, int
   if (order == 3) zoom_eval_kernel<3, true><<<grid, 128, 0, s>>>(work, side, out_side, mirror, map, scale);
   else zoom_eval_kernel<5, true><<<grid, 128, 0, s>>>(work, side, out_side, mirror, map, scale);
   launch_counter() += 2;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+extern "C" int bp_plane_prepare(int device, const float* raw, int rows, int cols, float add, float mul, float* out,
+                                void* stream) {
+  BP_REQUIRE(raw && out, BP_E_INVALID, "plane_prepare: null pointer");
+  BP_REQUIRE(rows > 0 && cols > 0, BP_E_INVALID, "plane_prepare: bad shape %d x %d", rows, cols);
+  BP_CUDA_TRY(cudaSetDevice(device));
+  const dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  BP_REQUIRE(grid.y <= 65535, BP_E_UNSUPPORTED, "plane_prepare: %d rows", rows);
+  plane_prepare_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(raw, rows, cols, add, mul, out);
+  launch_counter()++;
   BP_CUDA_TRY(cudaGetLastError());
   return BP_OK;
 }

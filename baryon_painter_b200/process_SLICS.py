@@ -99,6 +99,17 @@ class DeviceBackend:
         z = self.torch.zeros((2, n_pixel_plane, n_pixel_plane), dtype=self.torch.float64, device=self.device)
         return z
 
+    def prepare_plane(self, raw, add, mul):
+        """(raw.T + add) * mul in float32 on the device (the reference's plane preprocessing, :157-159 / :187-189):
+        raw (rows, cols) float32 host array -> (cols, rows) float32 device tensor."""
+        torch = self.torch
+        d_raw = torch.from_numpy(np.ascontiguousarray(raw, np.float32)).to(self.device)
+        out = torch.empty((raw.shape[1], raw.shape[0]), dtype=torch.float32, device=self.device)
+        self._lib.plane_prepare(self.device.index or 0, d_raw.data_ptr(), raw.shape[0], raw.shape[1], add, mul, out.data_ptr(),
+                                torch.cuda.current_stream(self.device).cuda_stream)
+        torch.cuda.current_stream(self.device).synchronize()       # `d_raw` may be freed after return
+        return out
+
     def extract_tiles(self, plane, shifts, tile_relative_size, n_pixel_tile, mode, expansion_factor=1):
         """``get_tile`` + ``scipy.ndimage.zoom(tile, n_pixel_tile / side, mode=mode)`` for a list of shifts, on the
         device (csrc/bp_zoom.cu): (n, n_pixel_tile, n_pixel_tile) float32 device tensor.  The plane is uploaded once
@@ -106,7 +117,9 @@ class DeviceBackend:
         torch = self.torch
         if expansion_factor < 1:
             raise ValueError("Expension factors < 1 not supported.")
-        if getattr(self, "_plane_key", None) != id(plane):
+        if isinstance(plane, torch.Tensor):                 # already on the device (prepare_plane)
+            self._plane_dev, self._plane_key = plane.contiguous(), id(plane)
+        elif getattr(self, "_plane_key", None) != id(plane):
             self._plane_dev = torch.from_numpy(np.ascontiguousarray(plane, np.float32)).to(self.device)
             self._plane_key = id(plane)
         n = plane.shape[0]
@@ -188,22 +201,39 @@ class DeviceBackend:
 # ---------------------------------------------------------------------------------------------------
 # plane sources
 # ---------------------------------------------------------------------------------------------------
-def _load_massplane(massplane_path, z, i, LOS):
+def _massplane_file(massplane_path, z, i, LOS):
     axes = ["xy", "xz", "yz"][i % 3]
-    fn = os.path.join(massplane_path, f"{z:.3f}proj_half_finer_{axes}.dat_LOS{LOS}")
-    plane = np.fromfile(fn, dtype=np.float32)[1:].reshape(N_PIXEL_MASSPLANE, -1).T
-    return fn, plane * np.float32(MASS_NORM)
+    return os.path.join(massplane_path, f"{z:.3f}proj_half_finer_{axes}.dat_LOS{LOS}")
 
 
-def _load_delta(delta_path, z, LOS, SLICS_density):
+def _delta_file(delta_path, z, LOS):
+    return os.path.join(delta_path, f"{z:.3f}delta.dat_bicubic_LOS{LOS}")
+
+
+def _load_massplane(massplane_path, z, i, LOS, be=None):
+    """Mass plane (reference :157-159): 12288^2 float32 after one header word, transposed, times MASS_NORM.  With a
+    device backend the transpose and the scaling run on the GPU (csrc/bp_zoom.cu: plane_prepare_kernel) and the
+    plane stays there for the tile extraction."""
+    fn = _massplane_file(massplane_path, z, i, LOS)
+    raw = np.fromfile(fn, dtype=np.float32)[1:].reshape(N_PIXEL_MASSPLANE, -1)
+    if be is not None and hasattr(be, "prepare_plane"):
+        return fn, be.prepare_plane(raw, 0.0, np.float32(MASS_NORM))
+    return fn, raw.T * np.float32(MASS_NORM)
+
+
+def _load_delta(delta_path, z, LOS, SLICS_density, be=None):
+    """Delta plane (reference :187-189): 7745^2 float32, transposed, ``+= 96`` (mean of the mass plane), ``*= MASS_NORM``."""
     if SLICS_density:
         import astropy.io.fits as fits
         fn = os.path.join(delta_path, f"{z:.3f}density_LOS{LOS}.fits")
         with fits.open(fn) as hdu:
             delta = hdu[0].data.T
         return fn, delta * (MASS_NORM / 64)
-    fn = os.path.join(delta_path, f"{z:.3f}delta.dat_bicubic_LOS{LOS}")
-    delta = np.fromfile(fn, dtype=np.float32).reshape(N_PIXEL_DELTA, -1).T
+    fn = _delta_file(delta_path, z, LOS)
+    raw = np.fromfile(fn, dtype=np.float32).reshape(N_PIXEL_DELTA, -1)
+    if be is not None and hasattr(be, "prepare_plane"):
+        return fn, be.prepare_plane(raw, 96.0, MASS_NORM)
+    delta = raw.T
     delta += 96          # mean of the mass plane
     delta *= MASS_NORM
     return fn, delta
@@ -256,7 +286,7 @@ def process_SLICS(painter,
                     shift = np.asarray(shifts_path)[i]
                 else:
                     shifts = np.loadtxt(os.path.join(shifts_path, f"random_shift_LOS{LOS}"))[::-1]
-                    fn, plane = _load_massplane(massplane_path, z_SLICS[i], i, LOS)
+                    fn, plane = _load_massplane(massplane_path, z_SLICS[i], i, LOS, be if not SLICS_density else None)
                     say(f"  Loading {fn}.")
                     shift = shifts[i]
                 say("  Extracting tile.")
@@ -278,7 +308,7 @@ def process_SLICS(painter,
         if plane_source is not None:
             delta = plane_source(i, "delta")
         else:
-            fn, delta = _load_delta(delta_path, z_SLICS[i], LOS, SLICS_density)
+            fn, delta = _load_delta(delta_path, z_SLICS[i], LOS, SLICS_density, be)
         n_pixel_plane = int(delta_size[i] / tile_size * n_pixel_tile)
         origins, slices = generate_tiling(n_pixel_plane=n_pixel_plane, n_pixel_tile=n_pixel_tile, min_tile_overlap=0.5)
         say(f"  Using {len(origins)} tiles (on each side)")

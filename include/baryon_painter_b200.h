@@ -167,6 +167,10 @@ int bp_zoom_tiles(int device, const float* plane, int plane_h, int plane_w, cons
  * for one float64 side x side painted plane; order 3 or 5; plane and map are device pointers. */
 int bp_zoom_accumulate(int device, const double* plane, int side, int out_side, int order, int mode, double scale,
                        double* map, void* stream);
+/* Plane preprocessing (reference process_SLICS.py:157-159, :187-189): the raw file is rows x cols float32, the
+ * reference takes `.T`, then `+= add`, then `*= mul` in float32:  out[c][r] = (raw[r][c] + add) * mul
+ * (two roundings, no fused multiply-add).  raw (after the caller skipped any header word) and out are device pointers. */
+int bp_plane_prepare(int device, const float* raw, int rows, int cols, float add, float mul, float* out, void* stream);
 
 /* ---- introspection ---------------------------------------------------------------------- */
 /* copy the activation after layer `layer` of sub-network `stack` (0 prior, 1 p_z_in, 2 p_y_z_in,

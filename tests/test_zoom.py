@@ -83,3 +83,25 @@ def test_gpu_zoom_tiles_match_scipy(mode):
         ref = scipy.ndimage.zoom(tile, zoom=128 / tile.shape[0], mode=mode)
         # float64 spline arithmetic on both sides, float32 result: a few ulp
         np.testing.assert_allclose(got[t], ref, rtol=3e-6, atol=3e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_plane_prepare_bit_identical_to_numpy():
+    """Plane preprocessing on the device (reference process_SLICS.py:157-159, :187-189): transpose, `+= 96`,
+    `*= MASS_NORM` -- the same two float32 roundings as numpy, so bit-identical."""
+    from baryon_painter_b200 import process_SLICS as ps
+    be = ps.DeviceBackend("cuda:0")
+    raw = (np.random.default_rng(3).standard_normal((301, 257)) * 40).astype(np.float32)
+    delta = raw.copy().T
+    delta += 96
+    delta *= ps.MASS_NORM
+    got = be.prepare_plane(raw, 96.0, ps.MASS_NORM).cpu().numpy()
+    assert got.shape == (257, 301) and np.array_equal(got, delta)
+    mass = raw.T * np.float32(ps.MASS_NORM)
+    assert np.array_equal(be.prepare_plane(raw, 0.0, np.float32(ps.MASS_NORM)).cpu().numpy(), mass)
+    # and the prepared plane feeds the tile extraction without leaving the device
+    tiles = be.extract_tiles(be.prepare_plane(raw, 96.0, ps.MASS_NORM), [(0.1, 0.8)], 0.4, 64, "reflect")
+    import scipy.ndimage
+    t = ps.get_tile(delta, shift=(0.1, 0.8), tile_relative_size=0.4)
+    ref = scipy.ndimage.zoom(t, zoom=64 / t.shape[0], mode="reflect")
+    np.testing.assert_allclose(tiles[0].cpu().numpy(), ref, rtol=3e-6, atol=3e-6 * np.abs(ref).max())
