@@ -1140,7 +1140,8 @@ static int paint_host_pipelined(bp_net* net, const float* tiles, float* out, int
   // still run in launches that fill the machine
   static const int env_step = getenv("BP_HOST_STEP") ? atoi(getenv("BP_HOST_STEP")) : 64;
   static const int env_edge = getenv("BP_HOST_EDGE") ? atoi(getenv("BP_HOST_EDGE")) : 16;
-  const int step = std::max(1, std::min(net->chunk, env_step));
+  int step = std::max(1, std::min(net->chunk, env_step));
+  if (n <= step && n >= 2 * env_edge && env_edge > 0) step = std::max(env_edge, (n + 3) / 4);   // small batch: still 2-4 chunks
   std::vector<int> bounds;
   {
     std::vector<int> head, tail;
