@@ -189,7 +189,7 @@ struct bp_net {
   float* params = nullptr;  // [3][max_batch] sigma_in, sigma_out, aux
   float *d_in = nullptr, *d_out = nullptr, *d_lat = nullptr;
   float *h_in = nullptr, *h_out = nullptr, *h_lat = nullptr;
-  float *var_mean = nullptr, *var_m2 = nullptr;
+  float *var_mean = nullptr, *var_m2 = nullptr, *var_rep = nullptr;   // variance maps: running moments, replicated tiles
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr, out_stream = nullptr;
   std::vector<cudaEvent_t> ev_ready, ev_chunk_done, ev_out;   // per chunk of the pipelined host path
@@ -247,7 +247,7 @@ static void destroy_net(bp_net* net) {
   for (int i = 0; i < 4; ++i) cudaFree(net->pool[i]);
   cudaFree(net->latent); cudaFree(net->prior_all); cudaFree(net->prior_keep); cudaFree(net->params);
   cudaFree(net->d_in); cudaFree(net->d_out); cudaFree(net->d_lat);
-  cudaFree(net->var_mean); cudaFree(net->var_m2);
+  cudaFree(net->var_mean); cudaFree(net->var_m2); cudaFree(net->var_rep);
   if (net->h_in) cudaFreeHost(net->h_in);
   if (net->h_out) cudaFreeHost(net->h_out);
   if (net->h_lat) cudaFreeHost(net->h_lat);
@@ -1400,26 +1400,67 @@ int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transf
   BP_CUDA_TRY(cudaMemcpyAsync(net->d_in, net->h_in, sizeof(float) * HW * n, cudaMemcpyHostToDevice, s));
   int rc = upload_params(net, tp, flags, n, s);
   if (rc != BP_OK) return rc;
+  // Draws are batched with tiles: a pass paints R draws of every tile of the group at once (the tiles and their
+  // transform parameters replicated R times), so the launches stay plan-chunk sized whatever the tile count --
+  // one 16-tile launch per draw ran the kernels at 60 % of their full-chunk rate.  (16-bit engine only: the fp32
+  // path keeps (y, z) of the front pass in place per batch entry.)
+  const bool can_rep = net->v2.built && !net->debug && !getenv("BP_VAR_NOREP");   // env: one draw per pass (test aid)
+  static const bool vtrace = getenv("BP_HOST_TRACE") != nullptr;
+  const auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double vt0 = now_ms();
   for (int c0 = 0; c0 < n; c0 += net->chunk) {
     const int nb = std::min(net->chunk, n - c0);
-    for (int d = 0; d < n_draws; ++d) {
-      // the prior depends only on the tile, but the rotating activation buffers are reused by the
-      // decoder, so (z_mu, z_log_var) are kept in prior_all after the first draw
-      float* prior_out = nullptr;
-      if (d == 0) {
-        rc = cvae_chunk_front(net, net->d_in, tp, flags, c0, nb, true, s, &prior_out);
-        if (rc != BP_OK) return rc;
-        BP_CUDA_TRY(cudaMemcpyAsync(net->prior_keep, prior_out, sizeof(float) * 2 * lhw * nb, cudaMemcpyDeviceToDevice, s));
-      }  // later draws: in_cat channel 0 is overwritten by p_z_in; channels 1-2 (y, z) stay valid
-      rc = launch_sample_z(net->prior_keep, nullptr, net->latent, nullptr, nullptr, net->min_z_var, nb, (int)lhw,
-                           BP_LATENT_SEED, seed, ((uint64_t)d * n + c0) * lhw, s);
+    const int R = can_rep ? std::max(1, std::min(n_draws, net->chunk / nb)) : 1;
+    rc = upload_params(net, tp, flags, n, s);              // (a previous group may have left replicated ones)
+    if (rc != BP_OK) return rc;
+    float* prior_out = nullptr;
+    rc = cvae_chunk_front(net, net->d_in, tp, flags, c0, nb, true, s, &prior_out);
+    if (rc != BP_OK) return rc;
+    for (int r = 0; r < R; ++r)
+      BP_CUDA_TRY(cudaMemcpyAsync(net->prior_keep + (size_t)r * nb * 2 * lhw, prior_out, sizeof(float) * 2 * lhw * nb,
+                                  cudaMemcpyDeviceToDevice, s));
+    bp_transform_params tpr = *tp;
+    std::vector<float> r_in, r_out, r_aux;
+    const float* rep_tiles = net->d_in;
+    int rep_c0 = c0;
+    if (R > 1) {
+      if (!net->var_rep) BP_CUDA_TRY(cudaMalloc(&net->var_rep, sizeof(float) * HW * net->chunk));
+      for (int r = 0; r < R; ++r) {
+        BP_CUDA_TRY(cudaMemcpyAsync(net->var_rep + (size_t)r * nb * HW, net->d_in + (size_t)c0 * HW, sizeof(float) * HW * nb,
+                                    cudaMemcpyDeviceToDevice, s));
+        for (int t = 0; t < nb; ++t) {
+          r_in.push_back(tp->sigma_in ? tp->sigma_in[c0 + t] : 0.f);
+          r_out.push_back(tp->sigma_out ? tp->sigma_out[c0 + t] : 0.f);
+          r_aux.push_back(tp->aux[c0 + t]);
+        }
+      }
+      tpr.sigma_in = tp->sigma_in ? r_in.data() : nullptr;
+      tpr.sigma_out = tp->sigma_out ? r_out.data() : nullptr;
+      tpr.aux = r_aux.data();
+      rc = upload_params(net, &tpr, flags, R * nb, s);
       if (rc != BP_OK) return rc;
-      rc = cvae_chunk_back(net, net->d_in, net->latent, tp, flags, c0, nb, net->d_out + (size_t)c0 * HW, s);
-      if (rc != BP_OK) return rc;
-      rc = launch_welford(net->d_out + (size_t)c0 * HW, net->var_mean + (size_t)c0 * HW,
-                          net->var_m2 + (size_t)c0 * HW, d + 1, HW * nb, s);
-      if (rc != BP_OK) return rc;
+      BP_CUDA_TRY(cudaStreamSynchronize(s));               // the replicated host vectors are read by the copies
+      rep_tiles = net->var_rep;
+      rep_c0 = 0;
     }
+    for (int d0 = 0; d0 < n_draws; d0 += R) {
+      const int Rd = std::min(R, n_draws - d0), ne = Rd * nb;
+      // counter-RNG offsets: group c0 owns [c0 * n_draws, (c0 + nb) * n_draws) * lhw, pass d0 a slice of it
+      rc = launch_sample_z(net->prior_keep, nullptr, net->latent, nullptr, nullptr, net->min_z_var, ne, (int)lhw,
+                           BP_LATENT_SEED, seed, ((uint64_t)c0 * n_draws + (uint64_t)d0 * nb) * lhw, s);
+      if (rc != BP_OK) return rc;
+      rc = cvae_chunk_back(net, rep_tiles, net->latent, R > 1 ? &tpr : tp, flags, rep_c0, ne, net->d_out, s);
+      if (rc != BP_OK) return rc;
+      for (int r = 0; r < Rd; ++r) {
+        rc = launch_welford(net->d_out + (size_t)r * nb * HW, net->var_mean + (size_t)c0 * HW, net->var_m2 + (size_t)c0 * HW,
+                            d0 + r + 1, HW * nb, s);
+        if (rc != BP_OK) return rc;
+      }
+    }
+  }
+  if (vtrace) {
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "[host] variance maps: %d tiles x %d draws painted in %.2f ms\n", n, n_draws, now_ms() - vt0);
   }
   rc = launch_var_finalize(net->var_m2, n_draws, HW * n, s);
   if (rc != BP_OK) return rc;

@@ -252,3 +252,21 @@ def test_host_pipeline_matches_device_call(n):
     assert np.isfinite(dev).all()
     assert np.array_equal(host, dev)
     assert np.array_equal(pin_out, dev)
+
+
+def test_variance_maps_draw_batching(monkeypatch):
+    """16-bit engine: draws are batched with tiles (R draws of every tile per pass).  Same counter-RNG stream and
+    the same sequential moment updates as one draw per pass, so the maps must be bit-identical."""
+    from baryon_painter_b200 import synthetic
+    p = _painter(64, 3, "fp16")
+    tiles = synthetic.synthetic_dm_tiles(3, 64, seed0=8)
+    zs = [0.0, 0.5, 1.0]
+    mean, var = p.paint_variance(tiles, z=zs, n_draws=10, seed=5)          # chunk 16 // 3 tiles -> 5 draws per pass
+    assert np.all(np.isfinite(mean)) and np.all(var >= 0) and var.max() > 0
+    monkeypatch.setenv("BP_VAR_NOREP", "1")
+    mean1, var1 = p.paint_variance(tiles, z=zs, n_draws=10, seed=5)
+    assert np.array_equal(mean, mean1) and np.array_equal(var, var1)
+    monkeypatch.delenv("BP_VAR_NOREP")
+    # a single draw is that draw, with zero variance
+    m, v = p.paint_variance(tiles, z=zs, n_draws=1, seed=5)
+    assert np.all(v == 0) and np.all(np.isfinite(m))
