@@ -302,8 +302,10 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
   }
 }
 
-template <int ACT, bool SKIP, bool OUTF32, int FMT>
-__global__ void __launch_bounds__(w_threads(SKIP || OUTF32), 1)
+// OUTF32: 0 = 16-bit NHWC output, 1 = fp32 plane written as float4 (segments of >= 4 pixels), 2 = fp32 plane with
+// 1- or 2-pixel segments (scalar stores; the register-heavy variant keeps the 384-thread CTA)
+template <int ACT, bool SKIP, int OUTF32, int FMT>
+__global__ void __launch_bounds__(w_threads(SKIP || OUTF32 == 2), 1)
 wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sP = smem;
@@ -323,14 +325,14 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
   long long tacc[4] = {0, 0, 0, 0};
   const long long t_start = a.timing ? clock64() : 0;
 
-  for (int i = tid; i < N; i += w_threads(SKIP || OUTF32)) s_shift[i] = a.shift[i];
+  for (int i = tid; i < N; i += w_threads(SKIP || OUTF32 == 2)) s_shift[i] = a.shift[i];
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full_p[s], 1);
       mbar_init(&empty_p[s], a.nissue);
       mbar_init(&tfull[s], a.nissue);
-      mbar_init(&tempty[s], 32 * w_epi_warps(SKIP || OUTF32));
+      mbar_init(&tempty[s], 32 * w_epi_warps(SKIP || OUTF32 == 2));
     }
     for (int s = 0; s < W_BSTAGES; ++s) {
       mbar_init(&full_b[s], 1);
@@ -425,7 +427,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     // quarter take every msplit-th M-tile and every (NEW / msplit)-th 16-column chunk.  One thread = one M row; a
     // chunk's two 8-column halves are 16-byte stores (one 32-byte store when both lie in one segment) to
     // row_base + seg_delta[segment] (+ channel).
-    constexpr int NEW = w_epi_warps(SKIP || OUTF32) / 4;
+    constexpr int NEW = w_epi_warps(SKIP || OUTF32 == 2) / 4;
     const int q = warp & 3;
     const int cpart = (warp - 4) >> 2;
     const int m = q * 32 + lane;
@@ -500,7 +502,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
-          if (OUTF32 && seg_shift < 2) {
+          if (OUTF32 == 2) {
             // fp32 plane, segments of 1 or 2 pixels (wide-input layers packed with G < 4): scalar stores
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
@@ -513,7 +515,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               reinterpret_cast<float*>(a.out)[rbase + a.seg_delta[seg] + ch] =
                   w_act<ACT>(__uint_as_float(v[e]) + s_shift[n0], act, act_param);
             }
-          } else if (OUTF32) {
+          } else if (OUTF32 == 1) {
             // fp32 output (single channel plane): segments of >= 4 columns, one float4 per quad
             const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
 #pragma unroll
@@ -913,17 +915,18 @@ typedef void (*WKernel)(const CUtensorMap, const WArgs);
 
 // instantiated variants: ReLU (+ residual), PReLU (16-bit / fp32 plane), generic activation switch; x operand format
 template <int FMT>
-static WKernel pick_kernel_fmt(int act, bool skip, bool f32) {
+static WKernel pick_kernel_fmt(int act, bool skip, int f32) {      // f32: the kernel's OUTF32 mode (0, 1, 2)
   if (act == BP_ACT_RELU && !f32)
-    return skip ? wconv_kernel<BP_ACT_RELU, true, false, FMT> : wconv_kernel<BP_ACT_RELU, false, false, FMT>;
+    return skip ? wconv_kernel<BP_ACT_RELU, true, 0, FMT> : wconv_kernel<BP_ACT_RELU, false, 0, FMT>;
   if ((act == BP_ACT_PRELU || act == BP_ACT_LEAKY) && !skip)
-    return f32 ? wconv_kernel<BP_ACT_PRELU, false, true, FMT> : wconv_kernel<BP_ACT_PRELU, false, false, FMT>;
+    return f32 == 2 ? wconv_kernel<BP_ACT_PRELU, false, 2, FMT>
+                    : f32 == 1 ? wconv_kernel<BP_ACT_PRELU, false, 1, FMT> : wconv_kernel<BP_ACT_PRELU, false, 0, FMT>;
   if ((act == BP_ACT_PRELU || act == BP_ACT_LEAKY) && !f32)          // LeakyReLU after the residual add (CGAN blocks)
-    return wconv_kernel<BP_ACT_PRELU, true, false, FMT>;
-  if (skip) return f32 ? nullptr : wconv_kernel<-1, true, false, FMT>;
-  return f32 ? wconv_kernel<-1, false, true, FMT> : wconv_kernel<-1, false, false, FMT>;
+    return wconv_kernel<BP_ACT_PRELU, true, 0, FMT>;
+  if (skip) return f32 ? nullptr : wconv_kernel<-1, true, 0, FMT>;
+  return f32 == 2 ? wconv_kernel<-1, false, 2, FMT> : f32 == 1 ? wconv_kernel<-1, false, 1, FMT> : wconv_kernel<-1, false, 0, FMT>;
 }
-static WKernel pick_kernel(int act, bool skip, bool f32, int fmt) {
+static WKernel pick_kernel(int act, bool skip, int f32, int fmt) {
   return fmt == 0 ? pick_kernel_fmt<0>(act, skip, f32) : pick_kernel_fmt<1>(act, skip, f32);
 }
 
@@ -953,7 +956,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   {
     // split of a region over the epilogue warps of one lane quarter: as many M-tile parts as T_r allows while a
     // warp keeps at most four 16-column chunks of an M-tile
-    const int new_ = w_epi_warps(skip != nullptr || out.f32) / 4;
+    const int new_ = w_epi_warps(skip != nullptr || (out.f32 && a.seg_shift < 2)) / 4;
     int ms = 1;
     while (ms * 2 <= new_ && ms * 2 <= a.T_r) ms *= 2;
     while (ms > 1 && ((a.N + 15) / 16 + new_ / ms - 1) / (new_ / ms) > 4) ms /= 2;
@@ -994,7 +997,8 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
                                      "window GEMM: segmented output into a space-to-depth layout");
   }
   const int grid = std::min(a.total_regions, g_w_sms);
-  WKernel k = pick_kernel(wl->act, skip != nullptr, out.f32, a.fmt);
+  const int f32_mode = !out.f32 ? 0 : (a.seg_shift < 2 ? 2 : 1);
+  WKernel k = pick_kernel(wl->act, skip != nullptr, f32_mode, a.fmt);
   BP_REQUIRE(k != nullptr, BP_E_UNSUPPORTED, "window GEMM: residual add with fp32 output");
   static const int dbg = getenv("BP_V2_DBG") ? atoi(getenv("BP_V2_DBG")) : 0;
   a.dbg = dbg;
@@ -1008,7 +1012,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   BP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_LIMIT));
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(w_threads(skip != nullptr || out.f32)); cfg.dynamicSmemBytes = wl->smem; cfg.stream = s;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(w_threads(skip != nullptr || f32_mode == 2)); cfg.dynamicSmemBytes = wl->smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
