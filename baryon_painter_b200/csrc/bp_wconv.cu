@@ -495,10 +495,9 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
           waited = true;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(T_r * N) + (uint32_t)(mt * N);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {             // at most 4 chunks per epilogue warp (N <= 128, or <= 64 split by M-tile)
-          const int c0 = cbase + k * cstep;
-          if (c0 >= N) break;
+        // one 16-column chunk; the loop over a warp's chunks is only unrolled where the residual prefetch needs
+        // compile-time indices (sk[k]): the epilogue is instruction-cache sensitive (ncu: no_inst stalls)
+        auto chunk = [&](const int k, const int c0) {
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -585,6 +584,16 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               if (ok[1]) *reinterpret_cast<uint4*>(ob16 + offs[1]) = o[1];
             }
           }
+        };
+        if (SKIP) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c0 = cbase + k * cstep;
+            if (c0 < N) chunk(k, c0);
+          }
+        } else {
+#pragma unroll 1
+          for (int c0 = cbase; c0 < N; c0 += cstep) chunk(0, c0);
         }
       }
       if (!waited) mbar_wait(&tfull[as], apar);   // a warp without an M-tile of its own still follows the phases
