@@ -35,7 +35,7 @@ using namespace tc;
 // epilogue warps: four per TMEM lane quarter, two for the residual variants (their 32-register prefetch of the
 // skip input does not fit the 96-register budget of a 640-thread CTA, and those layers are tensor-bound anyway)
 constexpr int W_MAX_SLOTS = 256;          // k-step slots of one phase and K block (tap lines x slices per line)
-// (`wide` = residual or fp32-plane variant: the register-heavy epilogues keep the 384-thread CTA)
+// (`wide` = residual variant: its register-heavy epilogue keeps the 384-thread CTA)
 constexpr int w_epi_warps(bool wide) { return wide ? 8 : 16; }
 constexpr int w_threads(bool wide) { return 128 + 32 * w_epi_warps(wide); }
 constexpr int W_PSTAGES = 2;
@@ -303,9 +303,9 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
 }
 
 // OUTF32: 0 = 16-bit NHWC output, 1 = fp32 plane written as float4 (segments of >= 4 pixels), 2 = fp32 plane with
-// 1- or 2-pixel segments (scalar stores; the register-heavy variant keeps the 384-thread CTA)
+// 1- or 2-pixel segments (scalar stores)
 template <int ACT, bool SKIP, int OUTF32, int FMT>
-__global__ void __launch_bounds__(w_threads(SKIP || OUTF32 == 2), 1)
+__global__ void __launch_bounds__(w_threads(SKIP), 1)
 wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sP = smem;
@@ -325,14 +325,14 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
   long long tacc[4] = {0, 0, 0, 0};
   const long long t_start = a.timing ? clock64() : 0;
 
-  for (int i = tid; i < N; i += w_threads(SKIP || OUTF32 == 2)) s_shift[i] = a.shift[i];
+  for (int i = tid; i < N; i += w_threads(SKIP)) s_shift[i] = a.shift[i];
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full_p[s], 1);
       mbar_init(&empty_p[s], a.nissue);
       mbar_init(&tfull[s], a.nissue);
-      mbar_init(&tempty[s], 32 * w_epi_warps(SKIP || OUTF32 == 2));
+      mbar_init(&tempty[s], 32 * w_epi_warps(SKIP));
     }
     for (int s = 0; s < W_BSTAGES; ++s) {
       mbar_init(&full_b[s], 1);
@@ -427,7 +427,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     // quarter take every msplit-th M-tile and every (NEW / msplit)-th 16-column chunk.  One thread = one M row; a
     // chunk's two 8-column halves are 16-byte stores (one 32-byte store when both lie in one segment) to
     // row_base + seg_delta[segment] (+ channel).
-    constexpr int NEW = w_epi_warps(SKIP || OUTF32 == 2) / 4;
+    constexpr int NEW = w_epi_warps(SKIP) / 4;
     const int q = warp & 3;
     const int cpart = (warp - 4) >> 2;
     const int m = q * 32 + lane;
@@ -965,7 +965,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   {
     // split of a region over the epilogue warps of one lane quarter: as many M-tile parts as T_r allows while a
     // warp keeps at most four 16-column chunks of an M-tile
-    const int new_ = w_epi_warps(skip != nullptr || (out.f32 && a.seg_shift < 2)) / 4;
+    const int new_ = w_epi_warps(skip != nullptr) / 4;
     int ms = 1;
     while (ms * 2 <= new_ && ms * 2 <= a.T_r) ms *= 2;
     while (ms > 1 && ((a.N + 15) / 16 + new_ / ms - 1) / (new_ / ms) > 4) ms /= 2;
@@ -1021,7 +1021,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   BP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_LIMIT));
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(w_threads(skip != nullptr || f32_mode == 2)); cfg.dynamicSmemBytes = wl->smem; cfg.stream = s;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(w_threads(skip != nullptr)); cfg.dynamicSmemBytes = wl->smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
