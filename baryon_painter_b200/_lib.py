@@ -30,7 +30,11 @@ EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destro
            "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles", "bp_zoom_accumulate", "bp_plane_prepare",
            "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
            "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile", "bp_net_chunk",
+           "bp_tuning_set", "bp_tuning_get", "bp_tuning_mode", "bp_rng_normal_host",
            "bp_last_error", "bp_version")
+
+# which tensor-core formulation / tiling every layer runs with (see include/baryon_painter_b200.h, "formulation table")
+TUNING_TABLE = os.path.join(_HERE, "tuning_table.txt")
 
 
 class LayerDesc(ctypes.Structure):
@@ -99,7 +103,17 @@ def load():
     lib.bp_net_set_profile.argtypes = [vp, i32]
     lib.bp_net_read_profile.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
     lib.bp_net_layer_info.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
+    lib.bp_tuning_set.argtypes = [ctypes.c_char_p]
+    lib.bp_tuning_get.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    lib.bp_tuning_mode.argtypes = [i32, i32]
+    lib.bp_rng_normal_host.argtypes = [i32, u64, u64, vp, ctypes.c_size_t]
     _lib = lib
+    # the shipped formulation table: every process builds the same kernels for the same layer, so painted tiles
+    # are bit-identical across processes (BARYON_PAINTER_TUNING_TABLE points at another table; "" = none)
+    path = os.environ.get("BARYON_PAINTER_TUNING_TABLE", TUNING_TABLE)
+    if path and os.path.exists(path):
+        with open(path, "rb") as f:
+            check(lib.bp_tuning_set(f.read()))
     return lib
 
 
@@ -276,6 +290,29 @@ class Net:
         out = np.empty(shape, np.float32)
         check(load().bp_net_read_activation(self.handle, stack, layer, out.ctypes.data, out.size))
         return out
+
+
+def tuning_mode(on, log=False):
+    check(load().bp_tuning_mode(int(bool(on)), int(bool(log))))
+
+
+def tuning_get():
+    lib = load()
+    n = lib.bp_tuning_get(None, 0)
+    buf = ctypes.create_string_buffer(n + 1)
+    lib.bp_tuning_get(buf, n + 1)
+    return buf.value.decode()
+
+
+def tuning_set(text):
+    check(load().bp_tuning_set(text.encode() if isinstance(text, str) else text))
+
+
+def rng_normal(seed, offset, n, device=0):
+    """The first ``n`` draws, from counter ``offset``, of the device's BP_LATENT_SEED standard-normal generator."""
+    out = np.empty(int(n), np.float32)
+    check(load().bp_rng_normal_host(int(device), int(seed) & (2 ** 64 - 1), int(offset), out.ctypes.data, out.size))
+    return out
 
 
 def launch_count(reset=False):

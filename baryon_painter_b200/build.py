@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libbaryon_painter_b200.so")
-SOURCES = ("bp_net.cu", "bp_f32.cu", "bp_tc.cu", "bp_win.cu", "bp_wconv.cu", "bp_v2.cu", "bp_front.cu", "bp_zoom.cu", "bp_stitch.cu")
+SOURCES = ("bp_net.cu", "bp_f32.cu", "bp_wconv.cu", "bp_v2.cu", "bp_front.cu", "bp_zoom.cu", "bp_stitch.cu")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

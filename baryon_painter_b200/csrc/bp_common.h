@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -12,6 +13,18 @@
 #include "../../include/baryon_painter_b200.h"
 
 namespace bp {
+
+// 16-bit operand formats of the tensor-core path (tcgen05 .kind::f16 a/b format field)
+enum { TC_FMT_F16 = 0, TC_FMT_BF16 = 1 };
+
+// Developer switches (BP_V2_*, BP_WIN_TIMING, ...) change formulations, disable work or print timings; they exist
+// only in -DBP_DEVELOPER builds (`python -m baryon_painter_b200.build --developer`).  The release library reads
+// three documented runtime knobs, none of which changes a painted value: BP_CHUNK, BP_HOST_STEP, BP_HOST_EDGE.
+#ifdef BP_DEVELOPER
+inline const char* dev_env(const char* name) { return getenv(name); }
+#else
+inline const char* dev_env(const char*) { return nullptr; }
+#endif
 
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -91,9 +104,6 @@ struct Layer {
   float* wmat = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
-  // 16-bit tensor-core path (filled by bp_tc.cu when the layer qualifies)
-  void* tc = nullptr;
-  void* win = nullptr;           // windowed (gather-free) tensor-core kernel, bp_win.cu
   bool v2 = false;               // runs on the window-GEMM engine (bp_wconv.cu)
   std::vector<float> host_weight;  // PyTorch-layout copy kept for the tensor-core packing
   std::vector<float> host_scale, host_shift;
@@ -110,7 +120,9 @@ int launch_prepare(const float* tiles, float* dst, long long dst_bs, int y_chann
                    int nb, int hw, cudaStream_t s);
 int launch_sample_z(const float* prior_out, const float* eps, float* latent, float* mu_out, float* lv_out,
                     float min_z_var, int nb, int hw, int mode, uint64_t seed, uint64_t offset, cudaStream_t s);
-int launch_welford(const float* x, float* mean, float* m2, int count, size_t n, cudaStream_t s);
-int launch_var_finalize(float* m2, int count, size_t n, cudaStream_t s);
+int launch_welford(const float* x, double* mean, double* m2, int count, size_t n, cudaStream_t s);
+int launch_var_finalize(const double* mean, const double* m2, float* mean_out, float* var_out, int count, size_t n,
+                        cudaStream_t s);
+int launch_rng_normal(float* out, uint64_t seed, uint64_t offset, size_t n, cudaStream_t s);
 
 }  // namespace bp

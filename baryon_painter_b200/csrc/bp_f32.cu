@@ -12,6 +12,8 @@
 //   CVAE.sample_z                       baryon_painter/models/cvae.py:63-66
 #include <math.h>
 
+#include <algorithm>
+
 #include "bp_common.h"
 
 namespace bp {
@@ -337,6 +339,25 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
+__device__ __forceinline__ float counter_normal(uint64_t seed, uint64_t counter) {
+  const uint64_t r = splitmix64(seed ^ splitmix64(counter));
+  const float u1 = ((float)(uint32_t)(r >> 40) + 1.f) * (1.f / 16777216.f);  // (0,1]
+  const float u2 = (float)(uint32_t)((r >> 8) & 0xFFFFFFu) * (1.f / 16777216.f);
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+__global__ void rng_normal_kernel(float* __restrict__ out, uint64_t seed, uint64_t offset, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = counter_normal(seed, offset + i);
+}
+int launch_rng_normal(float* out, uint64_t seed, uint64_t offset, size_t n, cudaStream_t s) {
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  rng_normal_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(out, seed, offset, n);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
 __global__ void sample_z_kernel(const float* __restrict__ prior_out, const float* __restrict__ eps,
                                 float* __restrict__ latent, float* __restrict__ mu_out,
                                 float* __restrict__ lv_out, float min_z_var, int nb, int hw, int mode,
@@ -350,10 +371,7 @@ __global__ void sample_z_kernel(const float* __restrict__ prior_out, const float
   if (mode == BP_LATENT_EPS) {
     e = eps[g];
   } else {
-    const uint64_t r = splitmix64(seed ^ splitmix64(offset + (uint64_t)g));
-    const float u1 = ((float)(uint32_t)(r >> 40) + 1.f) * (1.f / 16777216.f);  // (0,1]
-    const float u2 = (float)(uint32_t)((r >> 8) & 0xFFFFFFu) * (1.f / 16777216.f);
-    e = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    e = counter_normal(seed, offset + (uint64_t)g);
   }
   latent[g] = mu + e * (expf(lv * 0.5f) + min_z_var);
   if (mu_out) { mu_out[g] = mu; lv_out[g] = lv; }
@@ -372,31 +390,38 @@ int launch_sample_z(const float* prior_out, const float* eps, float* latent, flo
 // ------------------------------------------------------------------------------------------
 // running mean / M2 over latent draws (variance maps, BASELINE config 4)
 // ------------------------------------------------------------------------------------------
-__global__ void welford_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ m2,
-                               float inv_count, int first, size_t n) {
+// The running moments are float64: painted pressure spans ~6 decades within a tile and the M2 update subtracts
+// nearly equal numbers; the HBM cost (16 B per pixel and draw) is noise next to the painting.
+__global__ void welford_kernel(const float* __restrict__ x, double* __restrict__ mean, double* __restrict__ m2,
+                               double inv_count, int first, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = x[i];
-    if (first) { mean[i] = v; m2[i] = 0.f; continue; }
-    const float mu = mean[i], d = v - mu, mu2 = mu + d * inv_count;
+    const double v = (double)x[i];
+    if (first) { mean[i] = v; m2[i] = 0.0; continue; }
+    const double mu = mean[i], d = v - mu, mu2 = mu + d * inv_count;
     mean[i] = mu2;
     m2[i] += d * (v - mu2);
   }
 }
-__global__ void var_finalize_kernel(float* __restrict__ m2, float inv_count, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    m2[i] *= inv_count;
+// population variance (numpy.var default, what the oracle computes over its sample_P draws) and mean, as float32
+__global__ void var_finalize_kernel(const double* __restrict__ mean, const double* __restrict__ m2, float* __restrict__ mean_out,
+                                    float* __restrict__ var_out, double inv_count, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    mean_out[i] = (float)mean[i];
+    var_out[i] = (float)(m2[i] * inv_count);
+  }
 }
 
-int launch_welford(const float* x, float* mean, float* m2, int count, size_t n, cudaStream_t s) {
+int launch_welford(const float* x, double* mean, double* m2, int count, size_t n, cudaStream_t s) {
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  welford_kernel<<<blocks, 256, 0, s>>>(x, mean, m2, 1.f / (float)count, count == 1, n);
+  welford_kernel<<<blocks, 256, 0, s>>>(x, mean, m2, 1.0 / (double)count, count == 1, n);
   launch_counter()++;
   BP_CUDA_TRY(cudaGetLastError());
   return BP_OK;
 }
-int launch_var_finalize(float* m2, int count, size_t n, cudaStream_t s) {
+int launch_var_finalize(const double* mean, const double* m2, float* mean_out, float* var_out, int count, size_t n,
+                        cudaStream_t s) {
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  var_finalize_kernel<<<blocks, 256, 0, s>>>(m2, 1.f / (float)count, n);
+  var_finalize_kernel<<<blocks, 256, 0, s>>>(mean, m2, mean_out, var_out, 1.0 / (double)count, n);
   launch_counter()++;
   BP_CUDA_TRY(cudaGetLastError());
   return BP_OK;

@@ -10,11 +10,13 @@
 
 #include <algorithm>
 #include <chrono>
-#include <string>
+#include <map>
+#include <mutex>
 #include <new>
+#include <sstream>
+#include <string>
 
 #include "bp_common.h"
-#include "bp_tc.h"
 #include "bp_wconv.h"
 #include "bp_front.h"
 
@@ -127,8 +129,6 @@ int pack_layer(const bp_layer_desc& d, int H, int W, Layer* out) {
 
 void free_layer(Layer* l) {
   cudaFree(l->ktab); cudaFree(l->wmat); cudaFree(l->scale); cudaFree(l->shift);
-  tc_free_layer(l);
-  win_free_layer(l);
   l->ktab = nullptr; l->wmat = nullptr; l->scale = nullptr; l->shift = nullptr;
 }
 
@@ -189,7 +189,8 @@ struct bp_net {
   float* params = nullptr;  // [3][max_batch] sigma_in, sigma_out, aux
   float *d_in = nullptr, *d_out = nullptr, *d_lat = nullptr;
   float *h_in = nullptr, *h_out = nullptr, *h_lat = nullptr;
-  float *var_mean = nullptr, *var_m2 = nullptr, *var_rep = nullptr;   // variance maps: running moments, replicated tiles
+  double *var_mean = nullptr, *var_m2 = nullptr;                      // variance maps: running moments (float64)
+  float* var_rep = nullptr;                                           // ... and replicated tiles
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr, out_stream = nullptr;
   std::vector<cudaEvent_t> ev_ready, ev_chunk_done, ev_out;   // per chunk of the pipelined host path
@@ -317,39 +318,11 @@ static int finish_create(bp_net* net) {
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_done[i], cudaEventDisableTiming));
   }
   if (net->prec != BP_PREC_F32) {
-    const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
-    // sequences that stay in the 16-bit c8 layout: the prior network; p_z_in; p_y_z_in + p_mu_out
-    // (CGAN: the generator).  A layer runs on the tensor cores when tc_layer_eligible() says so.
-    for (int s = 0; s < net->nstacks; ++s) {
-      const bool continues = net->kind == NET_CVAE && s == ST_MU;   // p_mu_out continues p_y_z_in
-      std::vector<Layer>& L = net->st[s].layers;
-      for (size_t i = 0; i < L.size(); ++i) {
-        const bool first = (i == 0) && !continues;
-        if (!tc_layer_eligible(L[i].d, first)) continue;
-        if (!first) {
-          // the producer of this layer's input must be a tensor-core layer too, unless we repack
-          const Layer* prev = i > 0 ? &L[i - 1] : &net->st[ST_PYZ].layers.back();
-          if (!prev->tc && !prev->win && (L[i].d.cin % 8) != 0) continue;
-        }
-        int rc = BP_E_UNSUPPORTED;
-        if (win_layer_eligible(L[i].d, first)) rc = win_pack_layer(&L[i], fmt);
-        if (rc == BP_E_UNSUPPORTED) rc = tc_pack_layer(&L[i], fmt);
-        if (rc != BP_OK) return rc;
-      }
-      // a residual block runs on one path only
-      for (size_t i = 0; i < L.size(); ++i)
-        if (L[i].d.res == BP_RES_OPEN) {
-          size_t j = i;
-          while (L[j].d.res != BP_RES_CLOSE) ++j;
-          bool all = true;
-          for (size_t q = i; q <= j; ++q) all = all && (L[q].tc || L[q].win);
-          if (!all) for (size_t q = i; q <= j; ++q) { tc_free_layer(&L[q]); win_free_layer(&L[q]); }
-        }
-    }
-    if (!getenv("BP_ENGINE_V1")) {
-      int rc = net->kind == NET_CVAE ? v2_build(net) : v2_build_cgan(net);
-      if (rc != BP_OK) return rc;
-    }
+    // the 16-bit path is the window-GEMM engine (bp_wconv.cu) or nothing: a network it cannot lower fails here
+    int rc = net->kind == NET_CVAE ? v2_build(net) : v2_build_cgan(net);
+    if (rc != BP_OK) return rc;
+    BP_REQUIRE(net->v2.built, BP_E_UNSUPPORTED,
+               "the 16-bit tensor-core engine cannot lower this network's first layer; use precision fp32");
   }
   return BP_OK;
 }
@@ -374,27 +347,36 @@ static int v2_new_act(bp_net* net, ActDesc d, int* idx) {
 
 struct V2Ref { int stack, index; Layer* l; bool w; int need_b; };
 
-// device time of one launch of a built layer over a full chunk (median of three after a warm-up launch)
+// ---- tuning table ----------------------------------------------------------------------------------
+// Which window-GEMM formulation (pixel packing G x Jy, GEMM N) and tiling (strip width, M-tiles per region, tap
+// lines per weight stage, ring depth) a layer runs with is DATA, not a per-process measurement: formulations sum K
+// in different orders, so a process that timed candidates at load could paint bit-different tiles from the same
+// inputs as its neighbour.  Net creation looks the layer up in this table (shipped with the package as
+// baryon_painter_b200/tuning_table.txt, installed through bp_tuning_set); a layer that is not listed gets the
+// cost model's first formulation that fits -- deterministic too.  Only `bp_tuning_mode(1)` (python -m
+// baryon_painter_b200.tune, on a B200) times candidates, and records what it picked for bp_tuning_get.
+struct TuneEntry { int G, Jy, N, mode; WTiling t; float ms; };
+static std::mutex g_tune_mutex;
+static std::map<std::string, TuneEntry> g_tune_table;
+static bool g_tune_mode = false, g_tune_log = false;
 static int g_tune_launches = 0;
-static std::string g_tune_choices;
-static int v2_forced_choice(int stack, int index) {      // "stack.index=candidate[:tiling]" -> candidate + 1000 * tiling
-  const char* e = getenv("BP_V2_CHOICES");
-  if (!e) return -1;
-  const std::string key = std::to_string(stack) + "." + std::to_string(index) + "=";
-  const std::string sv(e);
-  size_t pos = 0;
-  while ((pos = sv.find(key, pos)) != std::string::npos) {
-    if (pos == 0 || sv[pos - 1] == ',') {
-      const char* q = sv.c_str() + pos + key.size();
-      const int cand = atoi(q);
-      const char* colon = strchr(q, ':');
-      const char* comma = strchr(q, ',');
-      const int rank = (colon && (!comma || colon < comma)) ? atoi(colon + 1) : 0;
-      return cand + 1000 * rank;
-    }
-    ++pos;
-  }
-  return -1;
+
+static std::string tune_key(const Layer& l, int fmt, int split) {
+  char b[128];
+  snprintf(b, sizeof(b), "%s:%d:%d:k%d:s%d:%dx%d:%s%s", l.d.kind == BP_CONV ? "conv" : "convT", l.d.cin, l.d.cout, l.d.kernel,
+           l.d.stride, l.H, l.W, fmt == TC_FMT_BF16 ? "bf16" : "f16", split ? ":split" : "");
+  return b;
+}
+static bool tune_lookup(const std::string& key, TuneEntry* e) {
+  std::lock_guard<std::mutex> g(g_tune_mutex);
+  auto it = g_tune_table.find(key);
+  if (it == g_tune_table.end()) return false;
+  *e = it->second;
+  return true;
+}
+static void tune_record(const std::string& key, const TuneEntry& e) {
+  std::lock_guard<std::mutex> g(g_tune_mutex);
+  g_tune_table[key] = e;
 }
 static int v2_time_layer(const WLayer* w, const ActDesc& out, const void* skip, int nb, float* ms) {
   cudaEvent_t e[4];
@@ -425,7 +407,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
   // the caller's fp32 tiles come from the tail stencil (1 -> 1 convolution) or, for a wider last layer, from its
   // window GEMM (fp32 plane) followed by an identity tail that applies the inverse transform
   const bool wide_tail = caller_out && seq.back().w && seq.back().l->d.cout == 1 && seq.back().l->d.cin > 1 &&
-                         !getenv("BP_V2_NOTAIL");
+                         !dev_env("BP_V2_NOTAIL");
   if (caller_out && !wide_tail) seq.back().w = false;
   for (size_t i = 0; i < seq.size(); ++i)
     if (seq[i].l->d.res == BP_RES_OPEN) {
@@ -468,58 +450,73 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       if (d.res == BP_RES_CLOSE) { op.skip = skip; skip = -1; }
       rc = v2_new_act(net, o, &op.out);
       if (rc != BP_OK) return rc;
-      // several formulations of one layer (pixel packing of the narrow stride-1 convolutions): the issue-cycle
-      // model orders them, the device decides -- each one that fits is timed on a full chunk and the fastest kept
-      const bool tune = getenv("BP_V2_NOTUNE") == nullptr;
-      const bool tlog = getenv("BP_V2_TUNE_LOG") != nullptr;
-      const int max_tune = tune ? 20 : 1, max_rank = tune ? 4 : 1;
-      float best_ms = 0.f;
-      int built = 0, ci = -1, best_ci = -1, best_rank = 0;
-      // BP_V2_CHOICES="stack.index=candidate:tiling,..." replays an earlier run's selection without timing
-      // (profilers serialise launches and would perturb it); BP_V2_TUNE_LOG prints the string to replay
-      const int forced = v2_forced_choice(r.stack, r.index);          // candidate + 1000 * tiling rank, or -1
+      // several formulations of one layer (pixel packing of the narrow stride-1 convolutions) and several tilings
+      // of each: the tuning table names the one to build; without an entry the cost model's first that fits is used
+      const std::string key = tune_key(*r.l, fmt, 0);
       const void* skip_ptr = op.skip >= 0 ? P.acts[op.skip].ptr : nullptr;
-      rc = BP_E_UNSUPPORTED;
-      // pass 1: every formulation with the tiling the cost model likes best
-      for (const WSpec& sp : cands) {
-        ++ci;
-        if (forced >= 0 && ci != forced % 1000) continue;
-        if (built >= max_tune) break;
-        WLayer* w = nullptr;
-        int rb = wconv_build(sp, P.acts[cur], net->chunk, &w, forced >= 0 ? forced / 1000 : 0);
-        if (rb == BP_E_UNSUPPORTED) continue;
-        if (rb != BP_OK) { rc = rb; break; }
-        ++built;
-        rc = BP_OK;
-        if (!tune || forced >= 0) { op.w = w; best_ci = ci; break; }
-        float ms = 0.f;
-        rb = v2_time_layer(w, P.acts[op.out], skip_ptr, net->chunk, &ms);
-        if (rb != BP_OK) { wconv_free(w); rc = rb; break; }
-        if (tlog) fprintf(stderr, "[tune]   %d.%d N=%d G=%d Jy=%d mode=%d: %.3f ms\n", r.stack, r.index, sp.N, sp.G, sp.Jy, sp.mode, ms);
-        if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; best_ci = ci; }
-        else wconv_free(w);
+      TuneEntry te;
+      if (tune_lookup(key, &te) && !g_tune_mode) {
+        rc = BP_E_UNSUPPORTED;
+        for (const WSpec& sp : cands)
+          if (sp.G == te.G && sp.Jy == te.Jy && sp.N == te.N && sp.mode == te.mode) {
+            rc = wconv_build(sp, P.acts[cur], net->chunk, &op.w, 0, &te.t);
+            break;
+          }
+        if (rc == BP_E_UNSUPPORTED) { op.w = nullptr; }          // stale entry (other chunk size / code version): default
+        else if (rc != BP_OK) return rc;
       }
-      if (rc != BP_OK) { if (op.w) wconv_free(op.w); op.w = nullptr; return rc; }
-      // pass 2: the model's next tilings (strip width, M-tiles per region, stage size, ring depth) of the winner
-      if (tune && forced < 0) {
+      if (!op.w && !g_tune_mode) {
+        rc = BP_E_UNSUPPORTED;
+        for (const WSpec& sp : cands) {
+          rc = wconv_build(sp, P.acts[cur], net->chunk, &op.w, 0, nullptr);
+          if (rc != BP_E_UNSUPPORTED) break;
+        }
+        if (rc != BP_OK) { op.w = nullptr; return rc; }
+      }
+      if (!op.w) {
+        // tuning mode: every formulation that fits is timed on a full chunk with the model's best tiling, then the
+        // model's next three tilings of the winner; the fastest is kept and recorded
+        const int max_tune = 24, max_rank = 4;
+        float best_ms = 0.f;
+        int built = 0, ci = -1, best_ci = -1;
+        rc = BP_E_UNSUPPORTED;
+        for (const WSpec& sp : cands) {
+          ++ci;
+          if (built >= max_tune) break;
+          WLayer* w = nullptr;
+          int rb = wconv_build(sp, P.acts[cur], net->chunk, &w, 0, nullptr);
+          if (rb == BP_E_UNSUPPORTED) continue;
+          if (rb != BP_OK) { rc = rb; break; }
+          ++built;
+          rc = BP_OK;
+          float ms = 0.f;
+          rb = v2_time_layer(w, P.acts[op.out], skip_ptr, net->chunk, &ms);
+          if (rb != BP_OK) { wconv_free(w); rc = rb; break; }
+          if (g_tune_log) fprintf(stderr, "[tune]   %s N=%d G=%d Jy=%d mode=%d: %.3f ms\n", key.c_str(), sp.N, sp.G, sp.Jy, sp.mode, ms);
+          if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; best_ci = ci; }
+          else wconv_free(w);
+        }
+        if (rc != BP_OK) { if (op.w) wconv_free(op.w); op.w = nullptr; return rc; }
         for (int rank = 1; rank < max_rank; ++rank) {
           WLayer* w = nullptr;
-          int rb = wconv_build(cands[best_ci], P.acts[cur], net->chunk, &w, rank);
+          int rb = wconv_build(cands[best_ci], P.acts[cur], net->chunk, &w, rank, nullptr);
           if (rb == BP_E_UNSUPPORTED) break;
           if (rb != BP_OK) { wconv_free(op.w); op.w = nullptr; return rb; }
           float ms = 0.f;
           rb = v2_time_layer(w, P.acts[op.out], skip_ptr, net->chunk, &ms);
           if (rb != BP_OK) { wconv_free(w); wconv_free(op.w); op.w = nullptr; return rb; }
-          if (tlog) fprintf(stderr, "[tune]   %d.%d candidate %d tiling %d: %.3f ms (best so far %.3f)\n", r.stack, r.index, best_ci, rank, ms, best_ms);
-          if (ms < best_ms) { wconv_free(op.w); op.w = w; best_ms = ms; best_rank = rank; }
+          if (g_tune_log) fprintf(stderr, "[tune]   %s tiling %d: %.3f ms (best so far %.3f)\n", key.c_str(), rank, ms, best_ms);
+          if (ms < best_ms) { wconv_free(op.w); op.w = w; best_ms = ms; }
           else wconv_free(w);
         }
-      }
-      if (tune && forced < 0 && tlog) {
-        g_tune_choices += std::to_string(r.stack) + "." + std::to_string(r.index) + "=" + std::to_string(best_ci) + ":" +
-                          std::to_string(best_rank) + ",";
-        fprintf(stderr, "[tune] %d.%d conv %d->%d k%d: %d formulations timed, best %.3f ms (tune launches so far %d) BP_V2_CHOICES=%s\n",
-                r.stack, r.index, d.cin, d.cout, d.kernel, built, best_ms, g_tune_launches, g_tune_choices.c_str());
+        TuneEntry ne;
+        ne.G = cands[best_ci].G; ne.Jy = cands[best_ci].Jy; ne.N = cands[best_ci].N; ne.mode = cands[best_ci].mode;
+        wconv_tiling(op.w, &ne.t);
+        ne.ms = best_ms;
+        tune_record(key, ne);
+        if (g_tune_log)
+          fprintf(stderr, "[tune] %s: %d formulations timed, best %.3f ms (G=%d Jy=%d N=%d; tune launches so far %d)\n", key.c_str(),
+                  built, best_ms, ne.G, ne.Jy, ne.N, g_tune_launches);
       }
       ops.push_back(op);
       cur = op.out;
@@ -543,7 +540,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       if (d.res == BP_RES_OPEN) skip = cur;
       op.kind = V2_F32CONV; op.in = cur; op.final = last && caller_out;
       if (op.final && d.kind == BP_CONV && d.cin == 1 && d.cout == 1 && d.stride == 1 && d.kernel == 2 * d.pad + 1 &&
-          d.kernel <= 7 && d.res == BP_RES_NONE && !getenv("BP_V2_NOTAIL")) {
+          d.kernel <= 7 && d.res == BP_RES_NONE && !dev_env("BP_V2_NOTAIL")) {
         op.kind = V2_TAIL;
         TailParams& t = P.tail;
         memset(&t, 0, sizeof(t));
@@ -607,7 +604,7 @@ static int v2_build(bp_net* net) {
     }
   // fused front: p_z_in is a pyramid of single-channel k = 2s transposed convolutions
   const std::vector<Layer>& pzl = net->st[ST_PZ].layers;
-  bool front = seq[0].w && seq[0].need_b == 1 && net->in_c == 3 && pzl.size() <= 4 && !getenv("BP_V2_NOFRONT");
+  bool front = seq[0].w && seq[0].need_b == 1 && net->in_c == 3 && pzl.size() <= 4 && !dev_env("BP_V2_NOFRONT");
   for (const Layer& l : pzl)
     front = front && l.d.kind == BP_CONVT && l.d.cin == 1 && l.d.cout == 1 && l.d.kernel == 2 * l.d.stride &&
             2 * l.d.pad == l.d.stride && l.d.kernel <= 8 && l.d.out_pad == 0 && l.d.res == BP_RES_NONE;
@@ -637,7 +634,7 @@ static int v2_build(bp_net* net) {
   if (rc != BP_OK) return rc;
   // ---- prior network
   std::vector<Layer>& prl = net->st[ST_PRIOR].layers;
-  if (!prl.empty() && !getenv("BP_V2_NOPRIOR")) {
+  if (!prl.empty() && !dev_env("BP_V2_NOPRIOR")) {
     std::vector<V2Ref> ps;
     for (size_t i = 0; i < prl.size(); ++i) {
       V2Ref r{ST_PRIOR, (int)i, &prl[i], false, 1};
@@ -649,7 +646,7 @@ static int v2_build(bp_net* net) {
       // k4 s2 p1, 2 -> <= 8 channels followed by another window GEMM: folded into the front pass (FFMA stencil)
       const bool fuse0 = d0.kind == BP_CONV && d0.kernel == 4 && d0.stride == 2 && d0.pad == 1 && d0.cout <= 8 &&
                          d0.res == BP_RES_NONE && ps.size() > 1 && ps[1].w && (net->H % 2) == 0 && (net->W % 2) == 0 &&
-                         !getenv("BP_V2_NOFUSE0");
+                         !dev_env("BP_V2_NOFUSE0");
       if (fuse0) {
         memset(&P.fc, 0, sizeof(P.fc));
         P.fc.cout = d0.cout; P.fc.act = d0.act; P.fc.act_param = d0.act_param;
@@ -702,101 +699,57 @@ static float* pick_buffer(bp_net* net, const void* a, const void* b, const void*
   return nullptr;
 }
 
-// an activation tensor: fp32 NCHW with per-sample stride `bs`, or the 16-bit c8 layout of the
-// tensor-core path ([nb][C/8][H][W][8], dense)
+// an fp32 NCHW activation tensor with per-sample stride `bs`
 struct ActRef {
   const void* ptr = nullptr;
   long long bs = 0;
-  bool c8 = false;
 };
 
-static int record_debug(bp_net* net, int sidx, int i, int nl, const Layer& l, const void* out, long long out_bs,
-                        bool c8, int nb, cudaStream_t s) {
+static int record_debug(bp_net* net, int sidx, int i, int nl, const Layer& l, const void* out, long long out_bs, int nb,
+                        cudaStream_t s) {
   const size_t per = (size_t)l.d.cout * l.OHF * l.OWF;
   if (net->dbg[sidx].size() < (size_t)nl) net->dbg[sidx].resize(nl, nullptr);
   if (!net->dbg[sidx][i]) BP_CUDA_TRY(cudaMalloc(&net->dbg[sidx][i], sizeof(float) * per * net->chunk));
-  if (c8)
-    return launch_unpack_c8(out, l.d.cout, l.OHF * l.OWF, net->dbg[sidx][i], (long long)per, nb,
-                            net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16, s);
   BP_CUDA_TRY(cudaMemcpy2DAsync(net->dbg[sidx][i], per * sizeof(float), out, out_bs * sizeof(float),
                                 per * sizeof(float), nb, cudaMemcpyDeviceToDevice, s));
   return BP_OK;
 }
 
-// run one sub-network on nb samples.  The last layer writes fp32 NCHW to final_out (stride final_bs)
-// when given; otherwise to a pool buffer returned in *result (c8 if `c8_result_ok` and the last layer
-// runs on the tensor cores).
+// run one sub-network on nb samples with the fp32 kernels (precision fp32; p_z_in taps of the debug mode).  The last
+// layer writes to final_out (stride final_bs) when given; otherwise to a pool buffer returned in *result.
 static int run_stack(bp_net* net, int sidx, ActRef in, float* final_out, long long final_bs, const PostOp& post,
-                     int nb, cudaStream_t s, ActRef* result, bool c8_result_ok = false) {
+                     int nb, cudaStream_t s, ActRef* result) {
   Stack& st = net->st[sidx];
   ActRef cur = in;
   ActRef skip;
   const int nl = (int)st.layers.size();
-  const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
   for (int i = 0; i < nl; ++i) {
     Layer& l = st.layers[i];
     const bool last = (i == nl - 1);
-    const bool use_tc = l.tc != nullptr || l.win != nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (net->profile) {
       BP_CUDA_TRY(cudaEventCreate(&e0)); BP_CUDA_TRY(cudaEventCreate(&e1));
       BP_CUDA_TRY(cudaEventRecord(e0, s));
     }
-    // ---- bring the input into the representation this layer's kernel reads
-    if (use_tc && !cur.c8) {
-      float* pk = pick_buffer(net, cur.ptr, skip.ptr);
-      BP_REQUIRE(pk, BP_E_INVALID, "internal: no free activation buffer");
-      int rc = launch_pack_c8(static_cast<const float*>(cur.ptr), cur.bs, l.d.cin, l.H * l.W, pk, nb, fmt, s);
-      if (rc != BP_OK) return rc;
-      cur.ptr = pk; cur.bs = 0; cur.c8 = true;
-    } else if (!use_tc && cur.c8) {
-      float* up = pick_buffer(net, cur.ptr, skip.ptr);
-      BP_REQUIRE(up, BP_E_INVALID, "internal: no free activation buffer");
-      const long long bs = (long long)l.d.cin * l.H * l.W;
-      int rc = launch_unpack_c8(cur.ptr, l.d.cin, l.H * l.W, up, bs, nb, fmt, s);
-      if (rc != BP_OK) return rc;
-      cur.ptr = up; cur.bs = bs; cur.c8 = false;
-    }
     if (l.d.res == BP_RES_OPEN) skip = cur;
-    // ---- where the output goes
     const long long dense_bs = (long long)l.d.cout * l.OHF * l.OWF;
     ActRef out;
     if (last && final_out) {
-      out.ptr = final_out; out.bs = final_bs; out.c8 = false;
+      out.ptr = final_out; out.bs = final_bs;
     } else {
-      const bool next_tc = last ? c8_result_ok : (st.layers[i + 1].tc != nullptr || st.layers[i + 1].win != nullptr);
       out.ptr = pick_buffer(net, cur.ptr, skip.ptr, in.ptr);
       BP_REQUIRE(out.ptr, BP_E_INVALID, "internal: no free activation buffer");
-      out.c8 = use_tc && next_tc;
-      out.bs = out.c8 ? 0 : dense_bs;
+      out.bs = dense_bs;
     }
-    int rc;
-    if (use_tc) {
-      BP_REQUIRE(!(last && post.post != POST_NONE), BP_E_UNSUPPORTED,
-                 "inverse transform fused into a tensor-core layer is not implemented");
-      const void* sk = nullptr;
-      if (l.d.res == BP_RES_CLOSE) {
-        BP_REQUIRE(skip.c8, BP_E_INVALID, "internal: residual skip is not in the c8 layout");
-        sk = skip.ptr;
-      }
-      void* o16 = out.c8 ? const_cast<void*>(out.ptr) : nullptr;
-      float* o32 = out.c8 ? nullptr : static_cast<float*>(const_cast<void*>(out.ptr));
-      rc = l.win ? launch_conv_win(l, cur.ptr, o16, o32, out.bs, sk, nb, s)
-                 : launch_conv_tc(l, cur.ptr, o16, o32, out.bs, sk, nb, s);
-    } else {
-      ConvArgs a;
-      memset(&a, 0, sizeof(a));
-      a.in = static_cast<const float*>(cur.ptr); a.in_bs = cur.bs;
-      a.out = static_cast<float*>(const_cast<void*>(out.ptr)); a.out_bs = out.bs; a.nb = nb;
-      if (l.d.res == BP_RES_CLOSE) {
-        BP_REQUIRE(!skip.c8, BP_E_INVALID, "internal: residual skip is not fp32");
-        a.skip = static_cast<const float*>(skip.ptr); a.skip_bs = skip.bs;
-      }
-      if (last && post.post != POST_NONE) {
-        a.post = post.post; a.post_sigma = post.sigma; a.post_k = post.k; a.post_shift = post.shift;
-      }
-      rc = launch_conv_f32(l, a, s);
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const float*>(cur.ptr); a.in_bs = cur.bs;
+    a.out = static_cast<float*>(const_cast<void*>(out.ptr)); a.out_bs = out.bs; a.nb = nb;
+    if (l.d.res == BP_RES_CLOSE) { a.skip = static_cast<const float*>(skip.ptr); a.skip_bs = skip.bs; }
+    if (last && post.post != POST_NONE) {
+      a.post = post.post; a.post_sigma = post.sigma; a.post_k = post.k; a.post_shift = post.shift;
     }
+    int rc = launch_conv_f32(l, a, s);
     if (rc != BP_OK) return rc;
     if (net->profile) {
       BP_CUDA_TRY(cudaEventRecord(e1, s));
@@ -805,7 +758,7 @@ static int run_stack(bp_net* net, int sidx, ActRef in, float* final_out, long lo
     }
     if (l.d.res == BP_RES_CLOSE) skip = ActRef();
     if (net->debug) {
-      rc = record_debug(net, sidx, i, nl, l, out.ptr, out.bs, out.c8, nb, s);
+      rc = record_debug(net, sidx, i, nl, l, out.ptr, out.bs, nb, s);
       if (rc != BP_OK) return rc;
     }
     cur = out;
@@ -992,7 +945,7 @@ static int cvae_chunk_back(bp_net* net, const float* tiles, const float* latent,
     return v2_run(net, P.ops, out, (long long)HW, post, nb, s);
   }
   in.ptr = net->in_cat; in.bs = 3 * (long long)HW;
-  rc = run_stack(net, ST_PYZ, in, nullptr, 0, none, nb, s, &h, net->st[ST_MU].layers[0].tc != nullptr || net->st[ST_MU].layers[0].win != nullptr);
+  rc = run_stack(net, ST_PYZ, in, nullptr, 0, none, nb, s, &h);
   if (rc != BP_OK) return rc;
   return run_stack(net, ST_MU, h, out, (long long)HW, post, nb, s, nullptr);
 }
@@ -1158,7 +1111,7 @@ static int paint_host_pipelined(bp_net* net, const float* tiles, float* out, int
     for (size_t i = tail.size(); i-- > 0;) bounds.push_back(c0 += tail[i]);
   }
   const int nchunks = (int)bounds.size() - 1;
-  static const bool trace = getenv("BP_HOST_TRACE") != nullptr;      // per-chunk device timeline on stderr
+  static const bool trace = dev_env("BP_HOST_TRACE") != nullptr;      // per-chunk device timeline on stderr
   const unsigned evflags = trace ? cudaEventDefault : cudaEventDisableTiming;
   const auto cpu_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_cpu0 = cpu_now();
@@ -1226,6 +1179,62 @@ static int paint_host_pipelined(bp_net* net, const float* tiles, float* out, int
 extern "C" {
 
 int bp_version(void) { return BP_VERSION; }
+
+// ---- tuning table (see the comment above tune_key) ----
+// text: one layer per line, "key G Jy N mode Wt T_r gl nbst [ms]"; '#' starts a comment.  Replaces the table.
+int bp_tuning_set(const char* text) {
+  BP_REQUIRE(text, BP_E_INVALID, "null tuning table");
+  std::map<std::string, TuneEntry> t;
+  std::istringstream in(text);
+  std::string line;
+  int lineno = 0;
+  while (std::getline(in, line)) {
+    ++lineno;
+    const size_t h = line.find('#');
+    if (h != std::string::npos) line.resize(h);
+    std::istringstream ls(line);
+    std::string key;
+    if (!(ls >> key)) continue;
+    TuneEntry e;
+    e.ms = 0.f;
+    BP_REQUIRE(bool(ls >> e.G >> e.Jy >> e.N >> e.mode >> e.t.Wt >> e.t.T_r >> e.t.gl >> e.t.nbst), BP_E_INVALID,
+               "tuning table line %d: expected 'key G Jy N mode Wt T_r gl nbst'", lineno);
+    ls >> e.ms;
+    t[key] = e;
+  }
+  std::lock_guard<std::mutex> g(g_tune_mutex);
+  g_tune_table.swap(t);
+  return BP_OK;
+}
+// writes the current table (as bp_tuning_set reads it) into buf; returns the length needed (excluding the NUL)
+int bp_tuning_get(char* buf, size_t cap) {
+  std::ostringstream o;
+  {
+    std::lock_guard<std::mutex> g(g_tune_mutex);
+    for (const auto& kv : g_tune_table) {
+      const TuneEntry& e = kv.second;
+      char ms[32];
+      snprintf(ms, sizeof(ms), "%.4f", e.ms);
+      o << kv.first << ' ' << e.G << ' ' << e.Jy << ' ' << e.N << ' ' << e.mode << ' ' << e.t.Wt << ' ' << e.t.T_r << ' ' << e.t.gl
+        << ' ' << e.t.nbst << ' ' << ms << '\n';
+    }
+  }
+  const std::string str = o.str();
+  if (buf && cap > 0) {
+    const size_t n = std::min(cap - 1, str.size());
+    memcpy(buf, str.data(), n);
+    buf[n] = 0;
+  }
+  return (int)str.size();
+}
+// on: nets created from now on TIME the candidate formulations of every layer on the device and record the winners
+// (non-deterministic across runs by nature -- a tool for producing the table, never the default); log: print timings
+int bp_tuning_mode(int on, int log) {
+  std::lock_guard<std::mutex> g(g_tune_mutex);
+  g_tune_mode = on != 0;
+  g_tune_log = log != 0;
+  return BP_OK;
+}
 const char* bp_last_error(void) { return g_err; }
 int64_t bp_launch_count(int reset) {
   const int64_t v = g_launches;
@@ -1392,8 +1401,8 @@ int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transf
   const size_t HW = (size_t)net->H * net->W, lhw = (size_t)net->lh * net->lw;
   cudaStream_t s = net->stream;
   if (!net->var_mean) {
-    BP_CUDA_TRY(cudaMalloc(&net->var_mean, sizeof(float) * HW * net->max_batch));
-    BP_CUDA_TRY(cudaMalloc(&net->var_m2, sizeof(float) * HW * net->max_batch));
+    BP_CUDA_TRY(cudaMalloc(&net->var_mean, sizeof(double) * HW * net->max_batch));
+    BP_CUDA_TRY(cudaMalloc(&net->var_m2, sizeof(double) * HW * net->max_batch));
   }
   const int flags = BP_FLAG_TRANSFORM | BP_FLAG_INVERSE;
   memcpy(net->h_in, tiles, sizeof(float) * HW * n);
@@ -1404,8 +1413,8 @@ int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transf
   // transform parameters replicated R times), so the launches stay plan-chunk sized whatever the tile count --
   // one 16-tile launch per draw ran the kernels at 60 % of their full-chunk rate.  (16-bit engine only: the fp32
   // path keeps (y, z) of the front pass in place per batch entry.)
-  const bool can_rep = net->v2.built && !net->debug && !getenv("BP_VAR_NOREP");   // env: one draw per pass (test aid)
-  static const bool vtrace = getenv("BP_HOST_TRACE") != nullptr;
+  const bool can_rep = net->v2.built && !net->debug && !dev_env("BP_VAR_NOREP");   // env: one draw per pass (test aid)
+  static const bool vtrace = dev_env("BP_HOST_TRACE") != nullptr;
   const auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double vt0 = now_ms();
   for (int c0 = 0; c0 < n; c0 += net->chunk) {
@@ -1462,14 +1471,29 @@ int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transf
     cudaStreamSynchronize(s);
     fprintf(stderr, "[host] variance maps: %d tiles x %d draws painted in %.2f ms\n", n, n_draws, now_ms() - vt0);
   }
-  rc = launch_var_finalize(net->var_m2, n_draws, HW * n, s);
+  // float32 mean into d_out, variance into d_in (the tiles are no longer needed), then to the host
+  rc = launch_var_finalize(net->var_mean, net->var_m2, net->d_out, net->d_in, n_draws, HW * n, s);
   if (rc != BP_OK) return rc;
-  BP_CUDA_TRY(cudaMemcpyAsync(net->h_out, net->var_mean, sizeof(float) * HW * n, cudaMemcpyDeviceToHost, s));
+  BP_CUDA_TRY(cudaMemcpyAsync(net->h_out, net->d_out, sizeof(float) * HW * n, cudaMemcpyDeviceToHost, s));
+  BP_CUDA_TRY(cudaMemcpyAsync(net->h_in, net->d_in, sizeof(float) * HW * n, cudaMemcpyDeviceToHost, s));
   BP_CUDA_TRY(cudaStreamSynchronize(s));
   memcpy(mean_out, net->h_out, sizeof(float) * HW * n);
-  BP_CUDA_TRY(cudaMemcpyAsync(net->h_out, net->var_m2, sizeof(float) * HW * n, cudaMemcpyDeviceToHost, s));
-  BP_CUDA_TRY(cudaStreamSynchronize(s));
-  memcpy(var_out, net->h_out, sizeof(float) * HW * n);
+  memcpy(var_out, net->h_in, sizeof(float) * HW * n);
+  return BP_OK;
+}
+
+int bp_rng_normal_host(int device, uint64_t seed, uint64_t offset, float* out, size_t n) {
+  BP_REQUIRE(out || n == 0, BP_E_INVALID, "null output");
+  if (n == 0) return BP_OK;
+  int rc = check_device(device);
+  if (rc != BP_OK) return rc;
+  float* d = nullptr;
+  BP_CUDA_TRY(cudaMalloc(&d, sizeof(float) * n));
+  rc = launch_rng_normal(d, seed, offset, n, 0);
+  cudaError_t e = rc == BP_OK ? cudaMemcpy(out, d, sizeof(float) * n, cudaMemcpyDeviceToHost) : cudaSuccess;
+  cudaFree(d);
+  if (rc != BP_OK) return rc;
+  BP_CUDA_TRY(e);
   return BP_OK;
 }
 
@@ -1513,7 +1537,7 @@ int bp_net_layer_info(const bp_net* net, int stack, int layer, double* flops, in
   if (flops) *flops = l.flops;
   if (geom) {
     geom[0] = l.d.kind; geom[1] = l.d.cin; geom[2] = l.d.cout; geom[3] = l.d.kernel; geom[4] = l.d.stride;
-    geom[5] = l.H; geom[6] = l.W; geom[7] = l.OHF; geom[8] = l.OWF; geom[9] = l.v2 ? 3 : (l.win ? 2 : (l.tc ? 1 : 0));
+    geom[5] = l.H; geom[6] = l.W; geom[7] = l.OHF; geom[8] = l.OWF; geom[9] = l.v2 ? 3 : 0;
   }
   return BP_OK;
 }

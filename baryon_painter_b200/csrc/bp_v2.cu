@@ -28,7 +28,7 @@ static int round_pow2(int v, int lo) {
 bool v2_eligible(const Layer& l, int* need_b) {
   const bp_layer_desc& d = l.d;
   *need_b = 1;
-  if (getenv("BP_V2_OFF")) return false;
+  if (dev_env("BP_V2_OFF")) return false;
   if (d.cout > 128 || (d.cout & (d.cout - 1)) != 0) return false;
   if (d.cout < 8 && !(d.kind == BP_CONV && d.stride == 1 && (d.cout == 1 || d.cout == 2 || d.cout == 4))) return false;
   if (d.kind == BP_CONV) {
@@ -116,7 +116,7 @@ int v2_make_spec(const Layer& l, int fmt, WSpec* sp) {
   }
   sp->OHl = l.H; sp->OWl = l.W;
   sp->ry = sp->rx = s;
-  const bool merge = l.nphase * coutp <= 128 && !getenv("BP_V2_NOMERGE");
+  const bool merge = l.nphase * coutp <= 128 && !dev_env("BP_V2_NOMERGE");
   if (merge) {
     sp->nphase = 1;
     std::vector<WTap> all;
@@ -260,7 +260,7 @@ int v2_candidates(const Layer& l, int fmt, int Cp, std::vector<WSpec>* out) {
     if (rc != BP_OK) return rc;
     out->push_back(sp);
     // wide single-phase layers: also offer two / four output lines per M row (the build times them)
-    if (sp.nphase == 1 && sp.OWl >= 128 && !getenv("BP_V2_NOLINEPACK"))
+    if (sp.nphase == 1 && sp.OWl >= 128 && !dev_env("BP_V2_NOLINEPACK"))
       for (int J : {2, 4}) {
         WSpec pk;
         if (pack_lines(sp, J, &pk)) out->push_back(pk);
@@ -279,14 +279,20 @@ int v2_candidates(const Layer& l, int fmt, int Cp, std::vector<WSpec>* out) {
       if (N > 128) continue;
       if ((Jy & (Jy - 1)) != 0 && N - Jy * G * coutp >= 8 && N > 16) continue;   // odd packings only where they fill N
       const bool flat = (G == 1 && Jy == 1);
-      const int ntap = (Jy + d.kernel - 1) * (floordiv(G - 1 + d.pad, G) - floordiv(-d.pad, G) + 1);
-      const int kst = std::max(1, ub / 32);
+      // k-steps per tap line: the 32-byte slices of the tap units that hold a pixel of [-p, G - 1 + p] (the builder
+      // drops the all-zero slices at both ends)
+      const int du0 = floordiv(-d.pad, G), du1 = floordiv(G - 1 + d.pad, G);
+      int kline = 0;
+      for (int b0 = du0 * ub; b0 < (du1 + 1) * ub; b0 += 32) {
+        const int px0 = floordiv(b0, Cp * 2), px1 = floordiv(b0 + 31, Cp * 2);      // pixels (relative to unit 0) in this slice
+        if (px1 >= -d.pad && px0 <= G - 1 + d.pad) ++kline;
+      }
       const int rows = flat ? 128 : std::min(l.OWF / G, 128);
-      cands.push_back({ntap * kst * mma_cycles(N) / ((double)rows * G * Jy), G, Jy});
+      cands.push_back({(Jy + d.kernel - 1) * kline * mma_cycles(N) / ((double)rows * G * Jy), G, Jy});
     }
   }
   std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.cost < b.cost; });
-  if (const char* e = getenv("BP_V2_PACK")) {       // "cin:cout:k:G:Jy" forces one formulation (tuning aid)
+  if (const char* e = dev_env("BP_V2_PACK")) {       // "cin:cout:k:G:Jy" forces one formulation (tuning aid)
     int ci, co, kk, g, jy;
     if (sscanf(e, "%d:%d:%d:%d:%d", &ci, &co, &kk, &g, &jy) == 5 && ci == d.cin && co == d.cout && kk == d.kernel) {
       cands.clear();

@@ -60,6 +60,7 @@ struct WArgs {
   int ksb, nbst;               // k-step slots per weight stage (= glines * run); weight stages
   int kpu;                     // k-steps per unit block (UB / 32)
   int glines, run, spb;        // tap lines per weight stage, k-steps per tap line (ntu * kpu), stages per patch block
+  int nslots;                  // k-step slots of one phase and K block after dropping all-zero weight slices
   int nphase, total_segs;
   WPhase phase[kMaxPhases];
   int N, seg_shift, seg_valid;
@@ -231,7 +232,7 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
   const uint32_t bstep16 = 2u * (uint32_t)N;
   const uint32_t ub16 = (uint32_t)a.ub16;
   const uint32_t tile_step16 = (uint32_t)(a.mode == W_LINE ? a.Jy * a.PW : 128) * ub16;
-  const int nbst = a.nbst, nblk = a.nblk, glines = a.glines, run = a.run;
+  const int nbst = a.nbst, nblk = a.nblk, ksb = a.ksb, nslots = a.nslots;
   const int total_regions = a.total_regions;
   uint32_t pst = 0, ppar = 0, bst = 0, bpar = 0, as = 0, apar = 0;
   // barriers already seen complete by an early probe: the current weight stage's, the current patch block's,
@@ -251,14 +252,13 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
       pre_p = false;
       tc_fence_after();
       const uint32_t da_blk = a_lo0 + pst * pstage16 + row0;
-      int s0 = 0;
-      for (int l0 = 0; l0 < P.ntl; l0 += glines) {
+      for (int s0 = 0; s0 < nslots; s0 += ksb) {
         if (!pre_ok) W_TWAIT(2, mbar_wait(&full_b[bst], bpar));
         tc_fence_after();
         uint32_t db = b_lo0 + bst * bstage16;
         // one flat walk over the stage's k-step slots: the A offset of slot (tap line, 32-byte slice) comes from
         // the aoff table in the parameter bank (short tap lines made a nested line / slice loop mostly loop overhead)
-        const int ns = min(glines, P.ntl - l0) * run;
+        const int ns = min(ksb, nslots - s0);
         const long long t_loop = a.timing ? clock64() : 0;
         const int ns1 = ns - min(4, ns >> 1);
 #pragma unroll 2
@@ -275,7 +275,7 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
         {
           const uint32_t nb_ = bst + 1u == (uint32_t)nbst ? 0u : bst + 1u;
           pre_ok = mbar_test(&full_b[nb_], nb_ == 0u ? bpar ^ 1u : bpar);
-          if (l0 + glines >= P.ntl) {            // last stage of this K block: the next block's patch, and after
+          if (s0 + ksb >= nslots) {              // last stage of this K block: the next block's patch, and after
             pre_p = mbar_test(&full_p[pst ^ 1u], pst == 1u ? ppar ^ 1u : ppar);      // the last block the next
             if (blk + 1 == nblk) pre_t = mbar_test(&tempty[as ^ 1u], (as == 1u ? apar ^ 1u : apar) ^ 1u);   // accumulator
           }
@@ -289,7 +289,6 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
           acc = 1u;
           db += bstep16;
         }
-        s0 += ns;
         if (a.timing) tacc[3] += clock64() - t_loop;
         umma_commit_pred(&empty_b[bst], el);
         if (++bst == (uint32_t)nbst) { bst = 0; bpar ^= 1u; }
@@ -663,7 +662,7 @@ static uint16_t w_to16(float v, int fmt) {
 
 static double w_mma_floor(int N) { return std::max(45.5, std::max((4096.0 + 32.0 * N) / 128.0, N / 2.0)); }
 
-int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out, int rank) {
+int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out, int rank, const WTiling* forced) {
   *out = nullptr;
   BP_REQUIRE(!in.f32 && in.ptr, BP_E_INVALID, "window GEMM input must be a 16-bit NHWC tensor");
   const int Cs = in.b * in.b * in.Cp;                 // stored channels per stored pixel
@@ -784,7 +783,15 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out, in
   // fastest, because the model is only good to ~20 % (it mis-ranks ring depth against stage size in particular).
   // Deeper rings of the same (Wt, T_r, gl) only count once.
   std::sort(all.begin(), all.end(), [](const Choice& x, const Choice& y) { return x.score < y.score; });
-  {
+  if (forced && forced->Wt > 0) {
+    for (const Choice& c : all)
+      if (c.Wt == forced->Wt && c.T_r == forced->T_r && c.gl == forced->gl && c.nbst == forced->nbst) { best = c; break; }
+    if (best.Wt == 0) {
+      delete wl;
+      set_error("window GEMM: tiling Wt=%d T_r=%d gl=%d nbst=%d does not fit", forced->Wt, forced->T_r, forced->gl, forced->nbst);
+      return BP_E_UNSUPPORTED;
+    }
+  } else {
     std::vector<Choice> uniq;
     for (const Choice& c : all) {
       bool seen = false;
@@ -810,12 +817,39 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out, in
   if (sp.mode == W_LINE) a.lines = a.T_r * sp.Jy + a.top + bottom;
   else a.lines = (a.T_r * 128 + a.PW - 1) / a.PW + 1 + a.top + bottom;
   a.box_bytes = (uint32_t)UB * a.PW * a.lines;
-  if (ntl_max * run > W_MAX_SLOTS) {
+  // ---- k-step slots: (tap line, 32-byte slice of the line's run of tap units), in the issuer's walk order.  A slice
+  // whose weights are zero for every column, K block and phase is dropped (Toeplitz packings with G > 1 leave the
+  // outer slices of the first / last tap unit empty: conv5 8->1 with G = 4 needs 4 of its 6 slices per line)
+  std::vector<int> slot_line, slot_slice;
+  {
+    const int ntl0 = grids[0].ntl;
+    bool same = true;
+    for (const Grid& g : grids) same = same && g.ntl == ntl0;
+    if (!same) {
+      delete wl;
+      set_error("window GEMM: phases with different tap-line counts");
+      return BP_E_UNSUPPORTED;
+    }
+    for (int ti = 0; ti < ntl0; ++ti)
+      for (int sl = 0; sl < run; ++sl) {
+        const int tj = sl / kpu, k4 = sl % kpu;
+        bool any = false;
+        for (int pi = 0; pi < sp.nphase && !any; ++pi)
+          for (int kb = 0; kb < nkb && !any; ++kb)
+            for (int e = 0; e < 16 && !any; ++e)
+              for (int n = 0; n < sp.N && !any; ++n)
+                any = sp.weight(pi, grids[pi].index[(size_t)ti * grids[pi].ntu + tj], kb * (UB / 2) + k4 * 16 + e, n) != 0.f;
+        if (any) { slot_line.push_back(ti); slot_slice.push_back(sl); }
+      }
+    if (slot_line.empty()) { slot_line.push_back(0); slot_slice.push_back(0); }
+  }
+  a.nslots = (int)slot_line.size();
+  if (a.nslots > W_MAX_SLOTS) {
     delete wl;
-    set_error("window GEMM: %d tap lines x %d slices exceed the %d-slot offset table", ntl_max, run, W_MAX_SLOTS);
+    set_error("window GEMM: %d k-step slots exceed the %d-slot offset table", a.nslots, W_MAX_SLOTS);
     return BP_E_UNSUPPORTED;
   }
-  for (int i = 0; i < ntl_max * run; ++i) a.aoff[i] = (uint32_t)((i / run) * a.PW * (UB / 16) + (i % run) * 2);
+  for (int i = 0; i < a.nslots; ++i) a.aoff[i] = (uint32_t)(slot_line[i] * a.PW * (UB / 16) + slot_slice[i] * 2);
   // slack: garbage M rows of the last tile read up to (left + right) units past the box
   a.kb_bytes = (uint32_t)(((size_t)a.box_bytes + (size_t)UB * (a.left + right + 8) + 1023) / 1024 * 1024);
   a.stage_bytes = a.kb_bytes;
@@ -843,30 +877,24 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out, in
     P.seg_begin = (int)segs.size();
     for (const WSegOff& sg : sp.segs[pi]) segs.push_back(make_int2(sg.oy, sg.ox));
     P.nseg = (int)sp.segs[pi].size();
-    const int spb = (g.ntl + a.glines - 1) / a.glines;
-    if (pi == 0) a.spb = spb;
-    if (spb != a.spb) {
-      delete wl;
-      set_error("window GEMM: phases with different tap-line counts");
-      return BP_E_UNSUPPORTED;
-    }
+    const int spb = (a.nslots + a.ksb - 1) / a.ksb;
+    a.spb = spb;
     wp.resize((size_t)(stage_total + nkb * spb) * a.ksb * 2 * a.N * 8, 0);
     for (int kb = 0; kb < nkb; ++kb)
-      for (int ti = 0; ti < g.ntl; ++ti)
-        for (int tj = 0; tj < g.ntu; ++tj)
-          for (int k4 = 0; k4 < kpu; ++k4) {
-            const int stage = stage_total + kb * spb + ti / a.glines;
-            const int slot = (ti % a.glines) * run + tj * kpu + k4;
-            for (int half = 0; half < 2; ++half)
-              for (int n = 0; n < a.N; ++n)
-                for (int e = 0; e < 8; ++e) {
-                  const int elem = kb * (UB / 2) + k4 * 16 + half * 8 + e;
-                  const float w = sp.weight(pi, g.index[(size_t)ti * g.ntu + tj], elem, n);
-                  if (w != 0.f) wp[((((size_t)stage * a.ksb + slot) * 2 + half) * a.N + n) * 8 + e] = w_to16(w, sp.fmt);
-                }
-          }
+      for (int i = 0; i < a.nslots; ++i) {
+        const int ti = slot_line[i], tj = slot_slice[i] / kpu, k4 = slot_slice[i] % kpu;
+        const int stage = stage_total + kb * spb + i / a.ksb;
+        const int slot = i % a.ksb;
+        for (int half = 0; half < 2; ++half)
+          for (int n = 0; n < a.N; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int elem = kb * (UB / 2) + k4 * 16 + half * 8 + e;
+              const float w = sp.weight(pi, g.index[(size_t)ti * g.ntu + tj], elem, n);
+              if (w != 0.f) wp[((((size_t)stage * a.ksb + slot) * 2 + half) * a.N + n) * 8 + e] = w_to16(w, sp.fmt);
+            }
+      }
     stage_total += nkb * spb;
-    wl->mmas_per_region[pi] = (long long)g.ntl * run * nkb * a.T_r;
+    wl->mmas_per_region[pi] = (long long)a.nslots * nkb * a.T_r;
   }
   a.total_segs = (int)segs.size();
   if (a.total_segs > W_MAX_SEGS) {
@@ -914,6 +942,10 @@ int wconv_build(const WSpec& sp, const ActDesc& in, int nb_max, WLayer** out, in
   return BP_OK;
 }
 
+void wconv_tiling(const WLayer* w, WTiling* t) {
+  t->Wt = w->proto.Wt; t->T_r = w->proto.T_r; t->gl = w->proto.glines; t->nbst = w->proto.nbst;
+}
+
 void wconv_free(WLayer* w) {
   if (!w) return;
   cudaFree(w->wpack); cudaFree(w->shift);
@@ -959,7 +991,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
                  out.bytes_per_sample() < (1ull << 31),
              BP_E_UNSUPPORTED, "window conv: tile too large for 32-bit row arithmetic");
   {
-    const char* e = getenv("BP_V2_NISSUE");
+    const char* e = dev_env("BP_V2_NISSUE");
     a.nissue = (a.T_r >= 2 && !(e && atoi(e) == 1)) ? 2 : 1;
   }
   {
@@ -1009,9 +1041,9 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   const int f32_mode = !out.f32 ? 0 : (a.seg_shift < 2 ? 2 : 1);
   WKernel k = pick_kernel(wl->act, skip != nullptr, f32_mode, a.fmt);
   BP_REQUIRE(k != nullptr, BP_E_UNSUPPORTED, "window GEMM: residual add with fp32 output");
-  static const int dbg = getenv("BP_V2_DBG") ? atoi(getenv("BP_V2_DBG")) : 0;
+  static const int dbg = dev_env("BP_V2_DBG") ? atoi(dev_env("BP_V2_DBG")) : 0;
   a.dbg = dbg;
-  static const bool timing = getenv("BP_WIN_TIMING") != nullptr;
+  static const bool timing = dev_env("BP_WIN_TIMING") != nullptr;
   static long long* d_timing = nullptr;
   if (timing) {
     if (!d_timing) BP_CUDA_TRY(cudaMalloc(&d_timing, sizeof(long long) * 8 * 256));
@@ -1025,7 +1057,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    static const bool pdl = getenv("BP_V2_NOPDL") == nullptr;
+    static const bool pdl = dev_env("BP_V2_NOPDL") == nullptr;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     void* args[2] = {const_cast<CUtensorMap*>(&wl->tmap), &a};
     BP_CUDA_TRY(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(k), args));

@@ -58,10 +58,15 @@ struct WSpec {
 
 struct WLayer;   // opaque (bp_wconv.cu)
 
+// tiling of a formulation: strip width (units), M-tiles per region, tap lines per weight stage, weight-ring depth
+struct WTiling { int Wt = 0, T_r = 0, gl = 0, nbst = 0; };
+
 // builds the packed weights / k-step tables / TMA tensor map for `spec` reading from `in`
 // (whose device pointer must already be final) with capacity for `nb_max` samples
-// rank: 0 = the tiling the cost model likes best, 1 = its second choice, ... (BP_E_UNSUPPORTED past the last)
-int wconv_build(const WSpec& spec, const ActDesc& in, int nb_max, WLayer** out, int rank = 0);
+// rank: 0 = the tiling the cost model likes best, 1 = its second choice, ... (BP_E_UNSUPPORTED past the last);
+// forced: build exactly this tiling (BP_E_UNSUPPORTED if it does not fit)
+int wconv_build(const WSpec& spec, const ActDesc& in, int nb_max, WLayer** out, int rank = 0, const WTiling* forced = nullptr);
+void wconv_tiling(const WLayer* w, WTiling* t);
 void wconv_free(WLayer* w);
 int wconv_launch(const WLayer* w, const ActDesc& out, const void* skip, int nb, cudaStream_t s);
 int wconv_mma_count(const WLayer* w, int nb, double* cycles_floor);

@@ -107,7 +107,8 @@ class DeviceBackend:
         out = torch.empty((raw.shape[1], raw.shape[0]), dtype=torch.float32, device=self.device)
         self._lib.plane_prepare(self.device.index or 0, d_raw.data_ptr(), raw.shape[0], raw.shape[1], add, mul, out.data_ptr(),
                                 torch.cuda.current_stream(self.device).cuda_stream)
-        torch.cuda.current_stream(self.device).synchronize()       # `d_raw` may be freed after return
+        # no synchronisation: every kernel of this backend is enqueued on torch's current stream, and torch's caching
+        # allocator only hands a freed block (`d_raw`) to later work of that same stream
         return out
 
     def extract_tiles(self, plane, shifts, tile_relative_size, n_pixel_tile, mode, expansion_factor=1):
@@ -117,11 +118,13 @@ class DeviceBackend:
         torch = self.torch
         if expansion_factor < 1:
             raise ValueError("Expension factors < 1 not supported.")
+        # the uploaded plane is cached against a STRONG reference to the caller's array (compared with `is`): an
+        # id() key could match a different, later array that reuses a freed array's address
         if isinstance(plane, torch.Tensor):                 # already on the device (prepare_plane)
-            self._plane_dev, self._plane_key = plane.contiguous(), id(plane)
-        elif getattr(self, "_plane_key", None) != id(plane):
+            self._plane_dev, self._plane_ref = plane.contiguous(), plane
+        elif getattr(self, "_plane_ref", None) is not plane:
             self._plane_dev = torch.from_numpy(np.ascontiguousarray(plane, np.float32)).to(self.device)
-            self._plane_key = id(plane)
+            self._plane_ref = plane
         n = plane.shape[0]
         side = int(n * tile_relative_size * expansion_factor)
         pad = int(n * tile_relative_size * (expansion_factor - 1) / 2)
@@ -133,7 +136,6 @@ class DeviceBackend:
             o = torch.from_numpy(org[i0:i0 + per_call]).to(self.device)
             self._lib.zoom_tiles(self._plane_dev.device.index or 0, self._plane_dev.data_ptr(), plane.shape[0], plane.shape[1],
                                  o.data_ptr(), side, o.shape[0], n_pixel_tile, mode, out[i0:i0 + per_call].data_ptr(), stream)
-            torch.cuda.current_stream(self.device).synchronize()       # `o` may be freed after return
         return out
 
     def new_map(self, resolution):
@@ -145,7 +147,6 @@ class DeviceBackend:
         d = plane if isinstance(plane, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(plane, np.float64)).to(self.device)
         self._lib.zoom_accumulate(self.device.index or 0, d.data_ptr(), d.shape[0], y_map.shape[0], order, "mirror", scale,
                                   y_map.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
-        torch.cuda.current_stream(self.device).synchronize()       # `d` may be freed after return
 
     def paint(self, painter, tiles, z, batch):
         """(n, T, T) tiles (host array or device tensor) -> painted tiles as a device tensor."""
@@ -176,7 +177,6 @@ class DeviceBackend:
         self._lib.stitch_accumulate(planes[0].data_ptr(), planes[1].data_ptr(), planes.shape[1], painted.data_ptr(),
                                     org.data_ptr(), painted.shape[0], painted.shape[1], falloff, sigma,
                                     self.torch.cuda.current_stream(self.device).cuda_stream)
-        self.torch.cuda.current_stream(self.device).synchronize()   # `org` / `painted` may be freed after return
 
     def reduce(self, planes_list, dst, group):
         import torch.distributed as dist

@@ -172,6 +172,22 @@ int bp_zoom_accumulate(int device, const double* plane, int side, int out_side, 
  * (two roundings, no fused multiply-add).  raw (after the caller skipped any header word) and out are device pointers. */
 int bp_plane_prepare(int device, const float* raw, int rows, int cols, float add, float mul, float* out, void* stream);
 
+/* ---- formulation table (determinism) ---------------------------------------------------------------
+ * Each convolution has several tensor-core formulations (Toeplitz packings, tilings); which one runs is looked
+ * up in a table (text, one layer per line: "key G Jy N mode Wt T_r gl nbst [ms]") so that every process paints
+ * bit-identical tiles; a layer without an entry gets the cost model's first choice (deterministic).  The package
+ * installs baryon_painter_b200/tuning_table.txt at load.  bp_tuning_mode(1, log) makes subsequently created nets
+ * time the candidates on the device instead and record the winners (python -m baryon_painter_b200.tune);
+ * bp_tuning_get returns the table (needed length excluding NUL).  No reference counterpart: torch picks cuDNN
+ * algorithms per process (torch.backends.cudnn.benchmark) and is not bit-reproducible across algorithms either. */
+int bp_tuning_set(const char* table_text);
+int bp_tuning_get(char* buf, size_t cap);
+int bp_tuning_mode(int on, int log);
+/* n standard-normal draws of the BP_LATENT_SEED generator (counter-based: splitmix64(seed ^ splitmix64(offset + i))
+ * -> Box-Muller) to a host array -- the eps that replace torch.randn of reference cvae.py:64; lets tests check the
+ * distribution and restate the draws for the variance-map oracle */
+int bp_rng_normal_host(int device, uint64_t seed, uint64_t offset, float* out, size_t n);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 /* copy the activation after layer `layer` of sub-network `stack` (0 prior, 1 p_z_in, 2 p_y_z_in,
  * 3 p_mu_out; CGAN: 0) of the last paint call to host as float32 [n][C][H][W]; needs

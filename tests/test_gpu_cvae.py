@@ -2,8 +2,8 @@
 (generated from the unmodified reference by oracle/make_golden.py) and against the oracle
 restatement on fresh seeded inputs.
 
-Tolerances (BASELINE.json north_star): fp32 path <= 1e-4 relative L2 per tile; bf16 path <= 1e-2
-relative L2 per tile and auto/cross power spectra within 1 %.
+Tolerances (BASELINE.json north_star): fp32 path <= 1e-4 relative L2 per tile; 16-bit path <= 1e-2
+relative L2 per tile and auto/cross power spectra within 1 % (asserted exactly so; see TOL below).
 """
 import os
 
@@ -14,30 +14,22 @@ from conftest import GOLDEN, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-# painted-tile tolerances.  fp32 and the 16-bit tensor-core path with fp16 operands meet the
-# north_star bounds (1e-4 / 1e-2).  With bf16 operands the network output x_mu is within 1e-2 but the
-# inverse transform exp(4x) amplifies absolute errors of x four-fold, so painted tiles with a large
-# dynamic range exceed 1e-2 (DESIGN.md "Precision"); bf16 is tested at 1e-2 on x_mu and 1e-1 painted.
-TOL = {"fp32": 1e-4, "fp16": 1e-2, "bf16": 1e-1}
+# painted-tile tolerances, exactly as north_star states them: fp32 path <= 1e-4, 16-bit path <= 1e-2 relative L2 per
+# tile (and auto / cross power spectra within 1 %, asserted below at 128^2 and at 512^2).  The shipped 16-bit path has
+# fp16 operands (fp32 accumulation in TMEM; same tensor rate as bf16, 8x finer rounding).  bf16 operands stay
+# selectable but are NOT the shipped 16-bit path: through the inverse transform p = (exp(4x) - 1) sigma an absolute
+# error dx of the network output becomes a relative error 4 dx, and bf16's 8-bit mantissa through 25 layers gives
+# dx ~ 5e-3: the network output x_mu meets 1e-2, painted tiles do not, and the suite asserts no looser painted
+# bound for it (DESIGN.md "Precision").
+TOL = {"fp32": 1e-4, "fp16": 1e-2}
 TOL_XMU = {"fp32": 1e-5, "fp16": 2e-3, "bf16": 1e-2}
 # layer-boundary tensors: fp32 accumulates ~1e-6 per layer; fp16 ~ 4e-4, bf16 ~ 3e-3 per layer
 TOL_LAYER = {"fp32": 2e-5, "fp16": 3e-3, "bf16": 2e-2}
 # (z_mu, z_log_var) of the t64 fixture are 2x2 maps with one or two non-zero entries after the ReLU, so a single
 # element's rounding through the four 16-bit prior layers is the whole norm
 TOL_PRIOR = {"fp32": 2e-5, "fp16": 3e-3, "bf16": 5e-2}
-PRECISIONS = ["fp32", "fp16", "bf16"]
-
-
-def painted_tol(precision, ref_tile, sigma_p):
-    """Painted tolerance of one tile.  The inverse transform p = (exp(4x) - 1) sigma turns an absolute error dx
-    of the network output into a relative error 4 dx of the pressure, and the per-tile L2 norm of a tile with a
-    single extreme peak is that one pixel.  The trained model's x_mu stays below ~3 (p/sigma < e^12); seeded
-    synthetic weights occasionally produce x_mu >= 3.5 (p/sigma > 1e6) in one pixel.  For such tiles the
-    16-bit bound is widened three-fold (the x_mu bound TOL_XMU is asserted unchanged); fp32 is unaffected."""
-    x_max = float(np.log(np.asarray(ref_tile, np.float64).max() / sigma_p + 1) / 4)
-    if precision != "fp32" and x_max > 3.5:
-        return 3 * TOL[precision]
-    return TOL[precision]
+PRECISIONS = ["fp32", "fp16"]
+ALL_FORMATS = ["fp32", "fp16", "bf16"]
 
 
 def _painter(tile, seed, precision, max_batch=8):
@@ -50,7 +42,7 @@ def _tiles(g, n):
     return synthetic.synthetic_dm_tiles(n, int(g["tile_size"]), seed0=int(g["tiles_seed0"]))
 
 
-@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("precision", ALL_FORMATS)
 def test_layer_boundaries_t64(precision):
     from baryon_painter_b200 import arch
     g = np.load(os.path.join(GOLDEN, "cvae_t64_layers.npz"))
@@ -58,7 +50,8 @@ def test_layer_boundaries_t64(precision):
     p.model.net.set_debug(True)
     tiles = _tiles(g, 1)
     out = p.paint(tiles[0], z=float(g["z"][0]), eps=g["eps"][0])
-    assert rel_l2(out, g["painted_E"][0]) <= TOL[precision]
+    if precision in TOL:
+        assert rel_l2(out, g["painted_E"][0]) <= TOL[precision]
     stack_ids = {"prior_network": 0, "p_z_in": 1, "p_y_z_in": 2, "p_mu_out": 3}
     worst = 0.0
     for name, sid in stack_ids.items():
@@ -96,15 +89,13 @@ def test_golden_t128(precision):
     out_e = p.paint_batch(tiles, z=zs, eps=g["eps"])
     out_l = p.paint_batch(tiles, z=zs, latents=g["eps"])
     for i in range(4):
-        sig = p.inverse_transform.gpu_params("pressure", float(zs[i]))[1]
-        assert rel_l2(out_e[i], g["painted_E"][i]) <= painted_tol(precision, g["painted_E"][i], sig), ("E", i)
-        assert rel_l2(out_l[i], g["painted_L"][i]) <= painted_tol(precision, g["painted_L"][i], sig), ("L", i)
+        assert rel_l2(out_e[i], g["painted_E"][i]) <= TOL[precision], ("E", i)
+        assert rel_l2(out_l[i], g["painted_L"][i]) <= TOL[precision], ("L", i)
     # one tile at a time through paint(), the reference entry point
     for i in range(4):
         o = p.paint(tiles[i], z=float(zs[i]), eps=g["eps"][i])
         assert o.shape == (128, 128) and o.dtype == np.float32
-        sig = p.inverse_transform.gpu_params("pressure", float(zs[i]))[1]
-        assert rel_l2(o, g["painted_E"][i]) <= painted_tol(precision, g["painted_E"][i], sig)
+        assert rel_l2(o, g["painted_E"][i]) <= TOL[precision]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -118,7 +109,7 @@ def test_golden_t512(precision):
     assert rel_l2(o_l, g["painted_L"][0]) <= TOL[precision]
 
 
-@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("precision", ALL_FORMATS)
 def test_vs_oracle_fresh_inputs(precision):
     """same seeded weights/tiles/latents through the oracle (CPU) and the CUDA path; ragged batch
     (5 tiles with chunking) and redshifts outside the stats table (clamped)."""
@@ -138,7 +129,9 @@ def test_vs_oracle_fresh_inputs(precision):
     ref = orc.paint_batch(tiles, zs, stats, eps=eps)
     out = p.paint_batch(tiles, z=zs, eps=eps)
     for i in range(5):
-        assert rel_l2(out[i], ref[i]) <= TOL[precision], i
+        assert np.isfinite(out[i]).all()
+        if precision in TOL:
+            assert rel_l2(out[i], ref[i]) <= TOL[precision], i
     # network output before the inverse transform
     xm = p.paint_batch(tiles, z=zs, eps=eps, inverse_transform=False)
     for i in range(5):
@@ -148,18 +141,57 @@ def test_vs_oracle_fresh_inputs(precision):
         return
     # power spectra (north_star: within 1 % for the 16-bit path)
     for i in range(5):
-        k, pa_ref = pseudo_Pofk(ref[i], ref[i])
-        _, pa = pseudo_Pofk(out[i], out[i])
-        _, pdm = pseudo_Pofk(tiles[i], tiles[i])
-        _, px_ref = pseudo_Pofk(tiles[i], ref[i])
-        _, px = pseudo_Pofk(tiles[i], out[i])
-        assert np.max(np.abs(pa / pa_ref - 1)) <= 0.01
-        # cross spectrum: relative where it is significantly non-zero, and everywhere within 1 % of the
-        # amplitude sqrt(P_dm P_p) (bins where the cross-correlation changes sign have no relative error)
-        amp = np.sqrt(pdm * pa_ref)
-        assert np.max(np.abs(px - px_ref) / amp) <= 0.01
-        big = np.abs(px_ref) > 0.1 * amp
-        assert big.sum() >= 3 and np.max(np.abs(px[big] / px_ref[big] - 1)) <= 0.01
+        assert_spectra_within_1pct(tiles[i], out[i], ref[i])
+
+
+def assert_spectra_within_1pct(dm, out, ref):
+    """north_star: pressure auto-power and DM-pressure cross-power spectrum each within 1 % of the reference's
+    (estimator: reference validation_plotting.py:120-121 settings, restated in oracle.pseudo_Pofk)."""
+    from oracle.cvae_oracle import pseudo_Pofk
+    k, pa_ref = pseudo_Pofk(ref, ref)
+    _, pa = pseudo_Pofk(out, out)
+    _, pdm = pseudo_Pofk(dm, dm)
+    _, px_ref = pseudo_Pofk(dm, ref)
+    _, px = pseudo_Pofk(dm, out)
+    assert np.max(np.abs(pa / pa_ref - 1)) <= 0.01
+    # cross spectrum: relative where it is significantly non-zero, and everywhere within 1 % of the
+    # amplitude sqrt(P_dm P_p) (bins where the cross-correlation changes sign have no relative error)
+    amp = np.sqrt(pdm * pa_ref)
+    assert np.max(np.abs(px - px_ref) / amp) <= 0.01
+    big = np.abs(px_ref) > 0.1 * amp
+    assert big.sum() >= 3 and np.max(np.abs(px[big] / px_ref[big] - 1)) <= 0.01
+
+
+def test_benchmark_shape_chunk_vs_oracle():
+    """The configuration bench.py times: fiducial 512^2 network, fp16, many tiles in ONE plan chunk (64 here: the
+    same kernels, tilings and chunked launch path as the 256-tile step; bench.py repeats this check on its own
+    256-tile batch and prints it as `parity`).  8 tiles spread over the chunk are compared with the oracle:
+    <= 1e-2 relative L2 per tile and auto / cross spectra within 1 % (north_star), on mixed redshifts."""
+    import torch
+    from oracle.cvae_oracle import CVAEOracle
+    from baryon_painter_b200 import arch, synthetic, transforms
+    torch.set_num_threads(os.cpu_count())
+    tile, n = 512, 64
+    A = arch.fiducial_cvae_architecture(tile)
+    sd = synthetic.synthetic_cvae_state_dict(A, seed=0)
+    stats = transforms.fiducial_stats()
+    orc = CVAEOracle(A, sd)
+    p = _painter(tile, 0, "fp16", max_batch=n)
+    assert p.model.net.chunk >= n                      # one chunk
+    base = synthetic.synthetic_dm_tiles(8, tile, seed0=7000)
+    tiles = np.ascontiguousarray(np.concatenate([base] * (n // 8)) * np.linspace(0.8, 1.25, n, dtype=np.float32)[:, None, None])
+    eps = synthetic.synthetic_latents(n, (tile // 32, tile // 32), seed=3)
+    zs = np.array([0.0, 0.25, 0.5, 1.0])[np.arange(n) % 4]
+    out = p.paint_batch(tiles, z=zs, eps=eps)
+    assert np.isfinite(out).all()
+    worst = 0.0
+    for i in (0, 9, 18, 27, 36, 45, 54, 63):
+        ref = orc.paint(tiles[i], float(zs[i]), stats, eps=eps[i:i + 1])
+        e = rel_l2(out[i], ref)
+        worst = max(worst, e)
+        assert e <= TOL["fp16"], (i, e)
+        assert_spectra_within_1pct(tiles[i], out[i], ref)
+    print("worst rel-L2 over 8 of 64 tiles (512^2, fp16, one chunk): %.2e" % worst)
 
 
 def test_api_semantics():
@@ -218,15 +250,79 @@ def test_checkpoint_roundtrip(tmp_path):
         q.model.load_state_dict(bad)
 
 
-def test_variance_maps():
-    p = _painter(64, 3, "fp32")
-    from baryon_painter_b200 import synthetic
-    tiles = synthetic.synthetic_dm_tiles(3, 64, seed0=8)
-    mean, var = p.paint_variance(tiles, z=[0.0, 0.5, 1.0], n_draws=16, seed=2)
-    assert mean.shape == var.shape == (3, 64, 64)
-    assert np.all(np.isfinite(mean)) and np.all(var >= 0) and var.max() > 0
-    mean2, var2 = p.paint_variance(tiles, z=[0.0, 0.5, 1.0], n_draws=16, seed=2)
+def test_seed_mode_rng_is_standard_normal_and_restated():
+    """BP_LATENT_SEED replaces torch.randn (reference cvae.py:64) by a counter-based generator.  (1) its draws are
+    N(0,1): moments, tail fractions and a Kolmogorov-Smirnov distance over 2^20 draws; distinct seeds / offsets are
+    uncorrelated; (2) oracle/rng_oracle.py restates it (the variance-map parity below feeds those eps to the oracle)."""
+    from math import erf, sqrt
+    from baryon_painter_b200 import _lib
+    from oracle.rng_oracle import counter_normal
+    n = 1 << 20
+    e = _lib.rng_normal(1234, 77, n).astype(np.float64)
+    assert abs(e.mean()) < 4.0 / np.sqrt(n) and abs(e.var() - 1) < 5e-3
+    assert abs((e ** 3).mean()) < 1e-2 and abs((e ** 4).mean() - 3) < 3e-2
+    for t, frac in ((1.0, 0.3173105), (2.0, 0.0455003), (3.0, 0.0026998)):
+        assert abs((np.abs(e) > t).mean() / frac - 1) < 0.05
+    xs = np.sort(e)
+    cdf = 0.5 * (1 + np.vectorize(erf)(xs[::64] / sqrt(2)))
+    assert np.max(np.abs(cdf - (np.arange(n)[::64] + 0.5) / n)) < 2.5e-3          # KS: ~1.4/sqrt(n) at 5 %
+    e2 = _lib.rng_normal(1235, 77, n).astype(np.float64)
+    e3 = _lib.rng_normal(1234, 77 + n, n).astype(np.float64)
+    assert abs((e * e2).mean()) < 5e-3 and abs((e * e3).mean()) < 5e-3 and abs((e[:-1] * e[1:]).mean()) < 5e-3
+    r = counter_normal(1234, 77, 4096)
+    assert np.max(np.abs(r - e[:4096])) < 2e-6
+
+
+@pytest.mark.parametrize("precision,n_draws,tol_mean,tol_var", [("fp32", 24, 1e-4, 1e-3), ("fp16", 64, 1e-2, 3e-2)])
+def test_variance_maps_vs_oracle(precision, n_draws, tol_mean, tol_var):
+    """BASELINE.json configs[3]: per-pixel mean / variance of the painted pressure over latent draws, against the
+    oracle = mean / population variance of that many `sample_P` paints (reference cvae.py:149-162) fed the SAME eps
+    (the device's counter generator restated in oracle/rng_oracle.py).  Tolerances: the per-tile bound of the
+    precision for the mean map; the variance map is a difference of nearly equal numbers, so it is held to
+    10x / 3x that (relative L2 over the map)."""
+    import torch
+    from oracle.cvae_oracle import CVAEOracle
+    from oracle.rng_oracle import variance_draw_eps
+    from baryon_painter_b200 import arch, synthetic, transforms
+    torch.set_num_threads(os.cpu_count())
+    tile, n, seed = 128, 3, 17
+    A = arch.fiducial_cvae_architecture(tile)
+    sd = synthetic.synthetic_cvae_state_dict(A, seed=4)
+    stats = transforms.fiducial_stats()
+    orc = CVAEOracle(A, sd)
+    p = _painter(tile, 4, precision, max_batch=64)
+    tiles = synthetic.synthetic_dm_tiles(n, tile, seed0=800)
+    zs = [0.0, 0.5, 1.0]
+    mean, var = p.paint_variance(tiles, z=zs, n_draws=n_draws, seed=seed)
+    assert mean.shape == var.shape == (n, tile, tile) and np.all(var >= 0) and var.max() > 0
+    eps = variance_draw_eps(seed, n, n_draws, (tile // 32, tile // 32))
+    for t in range(n):
+        draws = np.stack([orc.paint(tiles[t], zs[t], stats, eps=eps[d, t:t + 1]) for d in range(n_draws)]).astype(np.float64)
+        assert rel_l2(mean[t], draws.mean(0)) <= tol_mean, (t, rel_l2(mean[t], draws.mean(0)))
+        assert rel_l2(var[t], draws.var(0)) <= tol_var, (t, rel_l2(var[t], draws.var(0)))
+    mean2, var2 = p.paint_variance(tiles, z=zs, n_draws=n_draws, seed=seed)
     assert np.array_equal(mean, mean2) and np.array_equal(var, var2)
+
+
+def test_bit_identical_across_processes():
+    """Which tensor-core formulation a layer runs with comes from the shipped table (or the cost model), never from
+    a per-process timing: two fresh processes paint bit-identical tiles (the load-time tuner made
+    results process-dependent)."""
+    import hashlib
+    import subprocess
+    import sys
+    code = ("import sys, hashlib, numpy as np; sys.path.insert(0, %r);"
+            "from baryon_painter_b200 import synthetic; from baryon_painter_b200.painter import CVAEPainter;"
+            "p = CVAEPainter.synthetic(tile_size=256, seed=1, precision='fp16', max_batch=8);"
+            "t = synthetic.synthetic_dm_tiles(5, 256, seed0=60); e = synthetic.synthetic_latents(5, (8, 8), seed=2);"
+            "o = p.paint_batch(t, z=[0.0, 0.2, 0.5, 1.0, 2.0], eps=e);"
+            "print('DIGEST', hashlib.sha256(np.ascontiguousarray(o).tobytes()).hexdigest())") % os.path.dirname(os.path.dirname(GOLDEN))
+    digests = []
+    for _ in range(2):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1]
 
 
 @pytest.mark.parametrize("n", [1, 17, 100])
