@@ -15,10 +15,10 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbaryon_painter_b200.so")
 
 BP_OK, BP_E_INVALID, BP_E_UNSUPPORTED, BP_E_CUDA, BP_E_NO_DEVICE, BP_E_NOMEM = 0, -1, -2, -3, -4, -5
 BP_CONV, BP_CONVT = 0, 1
-BP_PREC_F32, BP_PREC_BF16, BP_PREC_F16 = 0, 1, 2
+BP_PREC_F32, BP_PREC_BF16, BP_PREC_F16, BP_PREC_F32_FFMA = 0, 1, 2, 3
 BP_LATENT_GIVEN, BP_LATENT_EPS, BP_LATENT_SEED = 0, 1, 2
 BP_FLAG_TRANSFORM, BP_FLAG_INVERSE = 1, 2
-PRECISIONS = {"fp32": BP_PREC_F32, "f32": BP_PREC_F32, "float32": BP_PREC_F32,
+PRECISIONS = {"fp32": BP_PREC_F32, "f32": BP_PREC_F32, "float32": BP_PREC_F32, "fp32-ffma": BP_PREC_F32_FFMA,
               "bf16": BP_PREC_BF16, "bfloat16": BP_PREC_BF16,
               "fp16": BP_PREC_F16, "f16": BP_PREC_F16, "float16": BP_PREC_F16}
 

@@ -487,10 +487,16 @@ __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restri
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     float v = fmaf(acc[e], tp.scale, tp.shift);
-    // 16-bit path only: fast exp / log (a few ulp) are far below its tolerance
-    if (tp.act == BP_ACT_SOFTPLUS) v = v > 20.f ? v : __logf(1.f + __expf(v));
-    else v = f_act(v, tp.act, tp.act_param);
-    if (tp.post) v = (__expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+    if (tp.precise) {
+      // fp32-accurate path: the library functions (<= 2 ulp), as the reference's torch / numpy float32 arithmetic
+      v = f_act(v, tp.act, tp.act_param);
+      if (tp.post) v = (expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+    } else {
+      // 16-bit path: fast exp / log (a few ulp) are far below its tolerance
+      if (tp.act == BP_ACT_SOFTPLUS) v = v > 20.f ? v : __logf(1.f + __expf(v));
+      else v = f_act(v, tp.act, tp.act_param);
+      if (tp.post) v = (__expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+    }
     o[e] = v;
   }
   float* dst = out + (size_t)n * out_bs + (size_t)y * W + x0 + tx;

@@ -26,6 +26,7 @@ struct TailParams {
   float act_param;
   int post;
   float post_k, post_shift;
+  int precise;               // fp32-accurate path: library expf / log1pf instead of the fast intrinsics
 };
 
 // prior_network.0 fused into the front pass: k4 s2 p1 convolution of the 2-channel [y, z] input to <= 8 channels

@@ -171,11 +171,13 @@ struct V2Plan {
   PzParams pz;
   TailParams tail;
   bool prior_conv0 = false;       // prior_network.0 runs inside the front kernel
+  bool prior_from_cat = false;    // split precision: the prior network reads [y, z] of in_cat through a layout conversion
   FrontConvParams fc;
 };
 
 struct bp_net {
   int device = 0, kind = NET_CVAE, prec = BP_PREC_F32, max_batch = 0, chunk = 0;
+  bool split = false;           // fp32-accurate tensor-core path: split-precision fp16 operands (BP_PREC_F32)
   int H = 0, W = 0, lh = 0, lw = 0, in_c = 0;
   float min_z_var = 1e-7f;
   Stack st[4];
@@ -278,6 +280,7 @@ static int check_device(int device) {
   return BP_OK;
 }
 
+extern "C" const char* bp_last_error(void);
 static int v2_build(bp_net* net);
 static int v2_build_cgan(bp_net* net);
 
@@ -285,13 +288,16 @@ static int finish_create(bp_net* net) {
   const size_t HW = (size_t)net->H * net->W;
   size_t mx = 0;
   net->flops_per_tile = 0;
+  // the rotating fp32 pool serves run_stack: every stack of the FFMA path, only p_z_in (debug taps, and the split
+  // path's decoder input) on the tensor-core paths
   for (int s = 0; s < net->nstacks; ++s) {
-    mx = std::max(mx, net->st[s].max_floats);
+    if (net->prec == BP_PREC_F32_FFMA || (net->kind == NET_CVAE && s == ST_PZ)) mx = std::max(mx, net->st[s].max_floats);
     for (auto& l : net->st[s].layers) net->flops_per_tile += l.flops;
   }
+  mx = std::max<size_t>(mx, 16);
   // chunk: keep the three rotating activation buffers of one chunk around L2 size (126 MB) so that
   // a layer's output is still cache-resident when the next layer reads it
-  int chunk = net->prec == BP_PREC_F32 ? 4 : 256;
+  int chunk = net->prec == BP_PREC_F32_FFMA ? 4 : 256;
   if (const char* e = getenv("BP_CHUNK")) chunk = std::max(1, atoi(e));
   net->chunk = std::min(chunk, net->max_batch);
   net->pool_floats = mx * net->chunk;
@@ -317,12 +323,12 @@ static int finish_create(bp_net* net) {
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_in[i], cudaEventDisableTiming));
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_done[i], cudaEventDisableTiming));
   }
-  if (net->prec != BP_PREC_F32) {
-    // the 16-bit path is the window-GEMM engine (bp_wconv.cu) or nothing: a network it cannot lower fails here
+  if (net->prec != BP_PREC_F32_FFMA) {
+    // the tensor-core paths (16-bit, and split-precision fp32) are the window-GEMM engine (bp_wconv.cu) or nothing: a network it cannot lower fails here
     int rc = net->kind == NET_CVAE ? v2_build(net) : v2_build_cgan(net);
     if (rc != BP_OK) return rc;
     BP_REQUIRE(net->v2.built, BP_E_UNSUPPORTED,
-               "the 16-bit tensor-core engine cannot lower this network's first layer; use precision fp32");
+               "the tensor-core engine cannot lower this network's first layer; use precision fp32-ffma");
   }
   return BP_OK;
 }
@@ -346,6 +352,10 @@ static int v2_new_act(bp_net* net, ActDesc d, int* idx) {
 }
 
 struct V2Ref { int stack, index; Layer* l; bool w; int need_b; };
+
+// split-precision activations are stored times 2^7: values down to ~2e-3 keep a normal fp16 lo half, the largest
+// representable activation is 511 (the paint networks' post-BN activations stay below ~50)
+constexpr int kSplitSexp = 7;
 
 // ---- tuning table ----------------------------------------------------------------------------------
 // Which window-GEMM formulation (pixel packing G x Jy, GEMM N) and tiling (strip width, M-tiles per region, tap
@@ -418,16 +428,16 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       for (size_t q = i; q <= j; ++q) seq[q].w = all;
     }
   int skip = -1;
-  for (size_t i = 0; i < seq.size(); ++i) {
+  for (int i = 0; i < (int)seq.size(); ++i) {
     V2Ref& r = seq[i];
     const bp_layer_desc& d = r.l->d;
-    const bool last = (i + 1 == seq.size());
+    const bool last = (i + 1 == (int)seq.size());
     V2Op op;
     op.stack = r.stack; op.index = r.index; op.l = r.l;
     if (r.w) {
       const int Cp = v2_padc(d.cin);
       if (P.acts[cur].f32) {
-        ActDesc a; a.C = d.cin; a.Cp = Cp; a.H = r.l->H; a.W = r.l->W; a.b = r.need_b;
+        ActDesc a; a.C = d.cin; a.Cp = Cp; a.H = r.l->H; a.W = r.l->W; a.b = r.need_b; a.split = net->split; a.sexp = net->split ? kSplitSexp : 0;
         V2Op cv; cv.kind = V2_TO_NHWC16; cv.in = cur;
         int rc = v2_new_act(net, a, &cv.out);
         if (rc != BP_OK) return rc;
@@ -441,9 +451,9 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       ActDesc o; o.C = d.cout; o.H = r.l->OHF; o.W = r.l->OWF;
       const bool next_w = !last && seq[i + 1].w;
       if (d.cout == 1) { o.f32 = true; o.Cp = 1; }
-      else { o.Cp = std::max(8, v2_padc(d.cout)); o.b = next_w ? seq[i + 1].need_b : 1; }   // 16-byte stores
+      else { o.Cp = std::max(8, v2_padc(d.cout)); o.b = next_w ? seq[i + 1].need_b : 1; o.split = net->split; o.sexp = net->split ? kSplitSexp : 0; }   // 16-byte stores
       std::vector<WSpec> cands;
-      int rc = v2_candidates(*r.l, fmt, Cp, &cands);
+      int rc = v2_candidates(*r.l, fmt, Cp, net->split, &cands);
       if (rc != BP_OK) return rc;
       op.kind = V2_WCONV; op.in = cur;
       r.l->v2 = true;
@@ -452,7 +462,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       if (rc != BP_OK) return rc;
       // several formulations of one layer (pixel packing of the narrow stride-1 convolutions) and several tilings
       // of each: the tuning table names the one to build; without an entry the cost model's first that fits is used
-      const std::string key = tune_key(*r.l, fmt, 0);
+      const std::string key = tune_key(*r.l, fmt, net->split ? 1 : 0);
       const void* skip_ptr = op.skip >= 0 ? P.acts[op.skip].ptr : nullptr;
       TuneEntry te;
       if (tune_lookup(key, &te) && !g_tune_mode) {
@@ -467,9 +477,26 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       }
       if (!op.w && !g_tune_mode) {
         rc = BP_E_UNSUPPORTED;
+        std::string why;
         for (const WSpec& sp : cands) {
           rc = wconv_build(sp, P.acts[cur], net->chunk, &op.w, 0, nullptr);
           if (rc != BP_E_UNSUPPORTED) break;
+          char b[64];
+          snprintf(b, sizeof(b), " [G=%d Jy=%d N=%d mode=%d: ", sp.G, sp.Jy, sp.N, sp.mode);
+          why += std::string(b) + bp_last_error() + "]";
+        }
+        if (rc == BP_E_UNSUPPORTED)
+          set_error("no window-GEMM formulation of %s fits:%s", key.c_str(), why.substr(0, 800).c_str());
+        if (rc == BP_E_UNSUPPORTED && d.res == BP_RES_NONE) {
+          // (e.g. a 9x9 convolution over 128-byte split-precision pixels: more k-step slots than the offset table
+          // holds) -- this one layer runs on the fp32 FFMA kernel instead, bridged by layout conversions
+          cudaFree(P.acts[op.out].ptr);
+          net->v2.owned.pop_back();
+          P.acts.pop_back();
+          r.l->v2 = false;
+          r.w = false;
+          --i;
+          continue;
         }
         if (rc != BP_OK) { op.w = nullptr; return rc; }
       }
@@ -526,6 +553,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
         TailParams& tp = P.tail;
         memset(&tp, 0, sizeof(tp));
         tp.k = 1; tp.w[0] = 1.f; tp.scale = 1.f; tp.shift = 0.f; tp.act = BP_ACT_NONE;
+        tp.precise = net->split ? 1 : 0;
         ops.push_back(t);
       }
     } else {
@@ -548,6 +576,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
         for (int q = 0; q < d.kernel * d.kernel; ++q) t.w[q] = r.l->host_weight[q];
         t.scale = r.l->host_scale[0]; t.shift = r.l->host_shift[0];
         t.act = d.act; t.act_param = d.act_param;
+        t.precise = net->split ? 1 : 0;
       }
       if (d.res == BP_RES_CLOSE) { op.skip = skip; skip = -1; }
       if (!op.final) {
@@ -578,14 +607,23 @@ static int v2_build_cgan(bp_net* net) {
   std::vector<V2Ref> seq;
   for (size_t i = 0; i < net->st[ST_GEN].layers.size(); ++i) {
     V2Ref r{ST_GEN, (int)i, &net->st[ST_GEN].layers[i], false, 1};
-    r.w = v2_eligible(*r.l, &r.need_b);
+    r.w = v2_eligible(*r.l, &r.need_b, net->split);
     seq.push_back(r);
   }
-  if (!seq[0].w || net->in_c != 2) return BP_OK;           // first layer not lowerable: keep the fp32-bridged engine
-  // generator input [x', z - 1] written straight into the first layer's NHWC layout by the front kernel
-  ActDesc a; a.C = 2; a.Cp = 4; a.H = net->H; a.W = net->W; a.b = seq[0].need_b;
-  int rc = v2_new_act(net, a, &P.dec_in);
-  if (rc != BP_OK) return rc;
+  if (!seq[0].w || net->in_c != 2) return BP_OK;           // first layer not lowerable (the caller reports it)
+  int rc;
+  if (net->split) {
+    // split precision: [x', z - 1] as fp32 planes (launch_prepare), brought into the split layout by a conversion
+    ActDesc in0;
+    in0.ptr = net->in_cat; in0.C = 2; in0.Cp = 2; in0.H = net->H; in0.W = net->W; in0.f32 = true;
+    P.acts.push_back(in0);
+    P.dec_in = (int)P.acts.size() - 1;
+  } else {
+    // generator input [x', z - 1] written straight into the first layer's NHWC layout by the front kernel
+    ActDesc a; a.C = 2; a.Cp = 4; a.H = net->H; a.W = net->W; a.b = seq[0].need_b;
+    rc = v2_new_act(net, a, &P.dec_in);
+    if (rc != BP_OK) return rc;
+  }
   rc = v2_build_seq(net, seq, P.dec_in, P.ops, true, nullptr);
   if (rc != BP_OK) return rc;
   P.built = true;
@@ -599,12 +637,13 @@ static int v2_build(bp_net* net) {
   for (int sidx : {ST_PYZ, ST_MU})
     for (size_t i = 0; i < net->st[sidx].layers.size(); ++i) {
       V2Ref r{sidx, (int)i, &net->st[sidx].layers[i], false, 1};
-      r.w = v2_eligible(*r.l, &r.need_b);
+      r.w = v2_eligible(*r.l, &r.need_b, net->split);
       seq.push_back(r);
     }
   // fused front: p_z_in is a pyramid of single-channel k = 2s transposed convolutions
   const std::vector<Layer>& pzl = net->st[ST_PZ].layers;
-  bool front = seq[0].w && seq[0].need_b == 1 && net->in_c == 3 && pzl.size() <= 4 && !dev_env("BP_V2_NOFRONT");
+  // (the fused front kernels use the fast log and write plain 16-bit pixels: 16-bit path only)
+  bool front = seq[0].w && seq[0].need_b == 1 && net->in_c == 3 && pzl.size() <= 4 && !net->split && !dev_env("BP_V2_NOFRONT");
   for (const Layer& l : pzl)
     front = front && l.d.kind == BP_CONVT && l.d.cin == 1 && l.d.cout == 1 && l.d.kernel == 2 * l.d.stride &&
             2 * l.d.pad == l.d.stride && l.d.kernel <= 8 && l.d.out_pad == 0 && l.d.res == BP_RES_NONE;
@@ -638,7 +677,7 @@ static int v2_build(bp_net* net) {
     std::vector<V2Ref> ps;
     for (size_t i = 0; i < prl.size(); ++i) {
       V2Ref r{ST_PRIOR, (int)i, &prl[i], false, 1};
-      r.w = v2_eligible(*r.l, &r.need_b);
+      r.w = v2_eligible(*r.l, &r.need_b, net->split);
       ps.push_back(r);
     }
     if (ps[0].w && prl[0].d.cin == 2) {
@@ -646,8 +685,16 @@ static int v2_build(bp_net* net) {
       // k4 s2 p1, 2 -> <= 8 channels followed by another window GEMM: folded into the front pass (FFMA stencil)
       const bool fuse0 = d0.kind == BP_CONV && d0.kernel == 4 && d0.stride == 2 && d0.pad == 1 && d0.cout <= 8 &&
                          d0.res == BP_RES_NONE && ps.size() > 1 && ps[1].w && (net->H % 2) == 0 && (net->W % 2) == 0 &&
-                         !dev_env("BP_V2_NOFUSE0");
-      if (fuse0) {
+                         !net->split && !dev_env("BP_V2_NOFUSE0");
+      if (net->split) {
+        // [y, z] = channels 1, 2 of in_cat (fp32 planes, per-sample stride 3 HW), converted to the split layout
+        ActDesc v;
+        v.ptr = net->in_cat + (size_t)net->H * net->W; v.C = 2; v.Cp = 2; v.H = net->H; v.W = net->W; v.f32 = true;
+        v.f32_bs = 3ll * net->H * net->W;
+        P.acts.push_back(v);
+        P.prior_in = (int)P.acts.size() - 1;
+        P.prior_from_cat = true;
+      } else if (fuse0) {
         memset(&P.fc, 0, sizeof(P.fc));
         P.fc.cout = d0.cout; P.fc.act = d0.act; P.fc.act_param = d0.act_param;
         for (int co = 0; co < d0.cout; ++co) {
@@ -877,7 +924,9 @@ static int cvae_chunk_front(bp_net* net, const float* tiles, const bp_transform_
   if (!need_prior) return BP_OK;
   PostOp none;
   if (v2_prior) {
-    if (P.prior_conv0)
+    if (P.prior_from_cat)
+      rc = BP_OK;                                  // launch_prepare above wrote [y, z]; prior_ops start with the conversion
+    else if (P.prior_conv0)
       rc = launch_front_prior_conv(tiles + (size_t)c0 * HW, P.acts[P.prior_in], net->params + c0, net->params + 2 * mb + c0,
                                    P.fc, tp->k_in, tp->shift_in, do_t, net->H, net->W, nb, fmt, s);
     else
@@ -1040,9 +1089,14 @@ static int cgan_paint_device(bp_net* net, const float* tiles, const bp_transform
         post2.post = POST_INV_SHIFT_LOG; post2.sigma = net->params + mb + c0;
         post2.k = tp->k_out; post2.shift = tp->shift_out;
       }
-      rc = launch_front_prior(tiles + (size_t)c0 * HW, net->v2.acts[net->v2.dec_in], net->params + c0,
-                              net->params + 2 * mb + c0, tp->k_in, tp->shift_in, (flags & BP_FLAG_TRANSFORM) ? 1 : 0, nb,
-                              net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16, s);
+      if (net->split)
+        rc = launch_prepare(tiles + (size_t)c0 * HW, net->in_cat, 2 * (long long)HW, 0, 1, net->params + c0,
+                            net->params + 2 * mb + c0, tp->k_in, tp->shift_in, (flags & BP_FLAG_TRANSFORM) ? 1 : 0, nb,
+                            (int)HW, s);
+      else
+        rc = launch_front_prior(tiles + (size_t)c0 * HW, net->v2.acts[net->v2.dec_in], net->params + c0,
+                                net->params + 2 * mb + c0, tp->k_in, tp->shift_in, (flags & BP_FLAG_TRANSFORM) ? 1 : 0, nb,
+                                net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16, s);
       if (rc != BP_OK) return rc;
       rc = v2_run(net, net->v2.ops, out + (size_t)c0 * HW, (long long)HW, post2, nb, s);
       if (rc != BP_OK) return rc;
@@ -1250,8 +1304,8 @@ int bp_device_count(void) {
 int bp_cvae_create(const bp_cvae_desc* d, int precision, int max_batch, int device, bp_net** out) {
   BP_REQUIRE(d && out, BP_E_INVALID, "null argument");
   *out = nullptr;
-  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16 || precision == BP_PREC_F16, BP_E_INVALID,
-             "bad precision %d", precision);
+  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16 || precision == BP_PREC_F16 || precision == BP_PREC_F32_FFMA,
+             BP_E_INVALID, "bad precision %d", precision);
   BP_REQUIRE(max_batch > 0, BP_E_INVALID, "max_batch must be positive");
   BP_REQUIRE(d->tile_h > 0 && d->tile_w > 0 && d->latent_h > 0 && d->latent_w > 0, BP_E_INVALID, "bad tile shape");
   BP_REQUIRE((d->tile_h * d->tile_w) % 4 == 0, BP_E_INVALID, "tile area must be a multiple of 4");
@@ -1261,6 +1315,7 @@ int bp_cvae_create(const bp_cvae_desc* d, int precision, int max_batch, int devi
   bp_net* net = new (std::nothrow) bp_net();
   BP_REQUIRE(net, BP_E_NOMEM, "out of host memory");
   net->device = device; net->kind = NET_CVAE; net->prec = precision; net->max_batch = max_batch;
+  net->split = precision == BP_PREC_F32;
   net->H = d->tile_h; net->W = d->tile_w; net->lh = d->latent_h; net->lw = d->latent_w;
   net->min_z_var = d->min_z_var; net->in_c = 3; net->nstacks = 4;
   do {
@@ -1304,14 +1359,15 @@ int bp_cgan_create(const bp_layer_desc* layers, int n_layers, int tile_h, int ti
                    int device, bp_net** out) {
   BP_REQUIRE(layers && out && n_layers > 0, BP_E_INVALID, "null argument");
   *out = nullptr;
-  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16 || precision == BP_PREC_F16, BP_E_INVALID,
-             "bad precision %d", precision);
+  BP_REQUIRE(precision == BP_PREC_F32 || precision == BP_PREC_BF16 || precision == BP_PREC_F16 || precision == BP_PREC_F32_FFMA,
+             BP_E_INVALID, "bad precision %d", precision);
   BP_REQUIRE(max_batch > 0 && tile_h > 0 && tile_w > 0 && (tile_h * tile_w) % 4 == 0, BP_E_INVALID, "bad shape");
   int rc = check_device(device);
   if (rc != BP_OK) return rc;
   bp_net* net = new (std::nothrow) bp_net();
   BP_REQUIRE(net, BP_E_NOMEM, "out of host memory");
   net->device = device; net->kind = NET_CGAN; net->prec = precision; net->max_batch = max_batch;
+  net->split = precision == BP_PREC_F32;
   net->H = tile_h; net->W = tile_w; net->in_c = 2; net->nstacks = 1;
   rc = build_stack(layers, n_layers, 2, tile_h, tile_w, &net->st[ST_GEN], "generator");
   if (rc == BP_OK) {
@@ -1413,7 +1469,8 @@ int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transf
   // transform parameters replicated R times), so the launches stay plan-chunk sized whatever the tile count --
   // one 16-tile launch per draw ran the kernels at 60 % of their full-chunk rate.  (16-bit engine only: the fp32
   // path keeps (y, z) of the front pass in place per batch entry.)
-  const bool can_rep = net->v2.built && !net->debug && !dev_env("BP_VAR_NOREP");   // env: one draw per pass (test aid)
+  // (the split-precision path keeps (y, z) of the front pass in in_cat per batch entry: one draw per pass there)
+  const bool can_rep = net->v2.built && net->v2.front_on && !net->debug && !dev_env("BP_VAR_NOREP");   // env: test aid
   static const bool vtrace = dev_env("BP_HOST_TRACE") != nullptr;
   const auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double vt0 = now_ms();

@@ -10,7 +10,8 @@ The reference writes ``model_meta`` with ``dill.dump`` (reference
 Everything the paint path needs from those closures is *data*: the mode strings,
 ``k_values``, ``eps`` and the per-redshift ``stats`` table.  This module walks the
 pickle with a restricted unpickler that never builds code objects and never
-imports anything outside numpy/collections, lifts the closure cells out and
+imports anything outside an exact whitelist of numpy reconstructors (``getattr`` in the stream
+only resolves on this module's inert stand-ins), lifts the closure cells out and
 re-binds them to :class:`baryon_painter_b200.transforms.CompiledTransform`.
 
 ``write_model_meta`` emits a plain-pickle dict with the same keys; the transform
@@ -84,17 +85,55 @@ def _load_type(name):
     return _Code
 
 
-def _import_module(name, safe=False):
-    # numpy scalars are pickled through numpy.core.multiarray.scalar
-    name = name.replace("numpy.core", "numpy._core") if np.__version__ >= "2" else name
-    if not name.startswith("numpy"):
+_NUMPY_MAJOR = int(np.__version__.split(".")[0])
+# the only modules a model_meta / transform pickle may name: numpy's scalar and array reconstructors
+_NUMPY_MODULES = {"numpy": "numpy", "numpy.core.multiarray": "numpy.core.multiarray",
+                  "numpy._core.multiarray": "numpy._core.multiarray", "numpy.core.numeric": "numpy.core.numeric",
+                  "numpy._core.numeric": "numpy._core.numeric"}
+_NUMPY_NAMES = ("dtype", "scalar", "ndarray", "_reconstruct", "_frombuffer")
+
+
+class _InertModule:
+    """What dill's ``_import_module`` yields here: a NAME, never the module object -- attribute lookups on it go
+    through :func:`_safe_getattr`, which resolves only the whitelisted numpy reconstructors."""
+
+    def __init__(self, name):
+        self.name = name
+
+
+def _numpy_module(name):
+    if name not in _NUMPY_MODULES:
         raise pickle.UnpicklingError("model_meta: refusing to import %r" % (name,))
+    if _NUMPY_MAJOR >= 2:                       # numpy 1.x pickles name numpy.core.*, moved to numpy._core in 2.x
+        name = name.replace("numpy.core", "numpy._core")
     return importlib.import_module(name)
+
+
+def _import_module(name, safe=False):
+    if name not in _NUMPY_MODULES and not name.startswith("baryon_painter."):
+        raise pickle.UnpicklingError("model_meta: refusing to import %r" % (name,))
+    return _InertModule(name)
+
+
+def _safe_getattr(obj, name, *default):
+    """``getattr`` for the pickle stream: only on the inert stand-ins of this module (never on a real module, class
+    or builtin, so no chain such as module -> os -> system can be walked)."""
+    if isinstance(obj, _InertModule):
+        if obj.name.startswith("baryon_painter."):
+            return {} if name == "__dict__" else _ByReference(obj.name, name)
+        if name in _NUMPY_NAMES:
+            return getattr(_numpy_module(obj.name), name)
+        raise pickle.UnpicklingError("model_meta: refusing attribute %s.%s" % (obj.name, name))
+    if isinstance(obj, (_Function, _ByReference, _Cell, _Code)):
+        if name.startswith("__") and name != "__dict__":
+            raise pickle.UnpicklingError("model_meta: refusing attribute %r" % (name,))
+        return getattr(obj, name, *default) if (default or hasattr(obj, name)) else {}
+    raise pickle.UnpicklingError("model_meta: refusing getattr on %s" % (type(obj).__name__,))
 
 
 class _MetaUnpickler(pickle.Unpickler):
     _DILL = {"_create_function": _Function, "_load_type": _load_type, "_create_cell": _Cell,
-             "_get_attr": getattr, "_import_module": _import_module}
+             "_get_attr": _safe_getattr, "_import_module": _import_module}
 
     def find_class(self, module, name):
         if module == "dill._dill" and name in self._DILL:
@@ -107,15 +146,16 @@ class _MetaUnpickler(pickle.Unpickler):
             return getattr(_tf, name)
         if (module, name) == ("collections", "OrderedDict"):
             return collections.OrderedDict
-        if module in ("numpy", "numpy.core.multiarray", "numpy._core.multiarray") and name in (
-                "dtype", "scalar", "ndarray", "_reconstruct"):
-            return getattr(_import_module(module), name)
+        if module in _NUMPY_MODULES and name in _NUMPY_NAMES:
+            return getattr(_numpy_module(module), name)
         if (module, name) == ("_codecs", "encode"):        # protocol-2 encoding of numpy scalar bytes
             import codecs
             return codecs.encode
         if module.endswith(".__dict__") or name == "__dict__":
             return {}
-        if module == "builtins" and name in ("getattr", "tuple", "list", "dict", "set", "float", "int"):
+        if (module, name) == ("builtins", "getattr"):
+            return _safe_getattr
+        if module == "builtins" and name in ("tuple", "list", "dict", "set", "float", "int"):
             return getattr(importlib.import_module("builtins"), name)
         raise pickle.UnpicklingError("model_meta: refusing global %s.%s" % (module, name))
 

@@ -24,7 +24,8 @@ import numpy as np
 from . import _lib, arch as _arch, meta as _meta, transforms as _tf
 
 # "fp16": 16-bit operands on the tcgen05 tensor cores (default); "bf16": same kernels, bf16 operands;
-# "fp32": FFMA kernels.  See DESIGN.md "Precision" for why fp16 is the default 16-bit format.
+# "fp32": fp32-accurate on the same tensor-core kernels (split-precision fp16 operands, fp32 accumulation);
+# "fp32-ffma": scalar FFMA kernels (cross-check).  See DESIGN.md "Precision".
 DEFAULT_PRECISION = os.environ.get("BARYON_PAINTER_PRECISION", "fp16")
 
 
@@ -272,6 +273,17 @@ class CVAEPainter(Painter):
             raise ValueError("tiles must be a contiguous float32 CUDA tensor")
         if out is None:
             out = torch.empty_like(tiles)
+        fusable = isinstance(self.transform, _tf.CompiledTransform) and self.transform.is_fusable(self.input_field) and \
+            isinstance(self.inverse_transform, _tf.CompiledTransform) and \
+            self.inverse_transform.is_fusable(self.label_fields[0]) and len(self.label_fields) == 1
+        if not fusable:
+            # no transforms in the checkpoint, or caller-installed ones the kernels cannot fuse: same semantics as
+            # paint_batch (the caller's callables applied on the host as the reference would), staged through the host
+            res = self.paint_batch(tiles.cpu().numpy(), z=z,
+                                   latents=None if latents is None else latents.cpu().numpy(),
+                                   eps=None if eps is None else eps.cpu().numpy(), seed=seed)
+            out.copy_(torch.from_numpy(np.ascontiguousarray(res, np.float32).reshape(out.shape)))
+            return out
         zs = np.broadcast_to(np.asarray(z, np.float64).reshape(-1), (n,))
         s_in, s_out, tp = self._sigmas(zs, True, True)
         flags = _lib.BP_FLAG_TRANSFORM | _lib.BP_FLAG_INVERSE

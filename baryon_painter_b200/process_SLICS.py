@@ -10,9 +10,11 @@ What changes is where the work runs:
     else the reference's one-tile ``paint`` loop), tiles staying on the device;
   * the Gaussian-edge weighted accumulation ``sum w*p / sum w`` runs on the device in float64 through the C ABI
     (``bp_stitch_accumulate`` / ``bp_stitch_finalize``);
-  * with ``world_size > 1`` the (plane, tile) work items are dealt round-robin to the ranks, every rank keeps
-    partial (numerator, denominator) planes, and ONE ``torch.distributed.reduce`` per run (NCCL over
-    NVLink on a GPU box) assembles them on rank 0 -- no collective while painting.
+  * with ``world_size > 1`` whole planes are dealt to the ranks by cost (``plan_planes``: 1 ... 144 tiles per plane);
+    a rank reads, uploads (page-locked staging, one plane ahead), paints and stitches only its own planes -- no
+    collective while painting.  ``paint_lightcone`` also projects each plane into the rank's partial Compton-y map
+    on its device and assembles the result with ONE reduction of that map (19 MB); ``process_SLICS`` (the
+    reference's contract: the planes themselves) sends each finished plane to rank 0 point to point.
 
 Additive keyword arguments (all optional): ``plane_source`` (callable returning in-memory planes instead of
 the SLICS files), ``rank`` / ``world_size`` / ``group`` (sharding), ``batch`` (tiles per paint call),
@@ -92,18 +94,49 @@ class DeviceBackend:
         _lib.load()                                        # fails loudly without the CUDA library
         if not torch.cuda.is_available():
             raise RuntimeError("baryon_painter_b200.process_SLICS needs a CUDA device; there is no CPU path")
+        import threading
         self.torch, self._lib = torch, _lib
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._copy_stream, self._staged, self._keep, self._stage_lock = None, {}, None, threading.Lock()
 
     def new_planes(self, n_pixel_plane):
         z = self.torch.zeros((2, n_pixel_plane, n_pixel_plane), dtype=self.torch.float64, device=self.device)
         return z
 
+    def stage(self, host):
+        """Host array -> device tensor through a page-locked buffer and an asynchronous copy on a side stream (the
+        caller's stream only waits for the copy's event): the upload of plane k+1 overlaps the painting of plane k
+        when this runs on ``_PlaneFeed``'s worker thread.  Device tensors pass through."""
+        torch = self.torch
+        if isinstance(host, torch.Tensor):
+            return host
+        host = np.ascontiguousarray(host)
+        with self._stage_lock:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            pinned = torch.empty(host.shape, dtype=getattr(torch, host.dtype.name), pin_memory=True)
+            pinned.numpy()[...] = host                      # (a file reader can fill `pinned` directly: read_into)
+            with torch.cuda.stream(self._copy_stream):
+                dev = pinned.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._staged[id(dev)] = (pinned, ev)            # keep the pinned source alive until the copy is consumed
+        return dev
+
+    def _consume(self, t):
+        """make the current stream wait for the asynchronous upload of ``t`` (if it came from ``stage``)"""
+        item = self._staged.pop(id(t), None)
+        if item is not None:
+            self.torch.cuda.current_stream(self.device).wait_event(item[1])
+            t.record_stream(self.torch.cuda.current_stream(self.device))
+            self._keep = item[0]                            # the pinned buffer may go once the NEXT plane is consumed
+        return t
+
     def prepare_plane(self, raw, add, mul):
         """(raw.T + add) * mul in float32 on the device (the reference's plane preprocessing, :157-159 / :187-189):
         raw (rows, cols) float32 host array -> (cols, rows) float32 device tensor."""
         torch = self.torch
-        d_raw = torch.from_numpy(np.ascontiguousarray(raw, np.float32)).to(self.device)
+        d_raw = self._consume(self.stage(np.asarray(raw, np.float32)))
         out = torch.empty((raw.shape[1], raw.shape[0]), dtype=torch.float32, device=self.device)
         self._lib.plane_prepare(self.device.index or 0, d_raw.data_ptr(), raw.shape[0], raw.shape[1], add, mul, out.data_ptr(),
                                 torch.cuda.current_stream(self.device).cuda_stream)
@@ -120,7 +153,8 @@ class DeviceBackend:
             raise ValueError("Expension factors < 1 not supported.")
         # the uploaded plane is cached against a STRONG reference to the caller's array (compared with `is`): an
         # id() key could match a different, later array that reuses a freed array's address
-        if isinstance(plane, torch.Tensor):                 # already on the device (prepare_plane)
+        if isinstance(plane, torch.Tensor):                 # already on the device (prepare_plane / stage)
+            self._consume(plane)
             self._plane_dev, self._plane_ref = plane.contiguous(), plane
         elif getattr(self, "_plane_ref", None) is not plane:
             self._plane_dev = torch.from_numpy(np.ascontiguousarray(plane, np.float32)).to(self.device)
@@ -178,24 +212,47 @@ class DeviceBackend:
                                     org.data_ptr(), painted.shape[0], painted.shape[1], falloff, sigma,
                                     self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def reduce(self, planes_list, dst, group):
+    def reduce(self, tensors, dst, group):
+        """ONE sum-reduction of a list of same-dtype device tensors to rank ``dst`` (NCCL over NVLink on a GPU box)"""
         import torch.distributed as dist
-        flat = self.torch.cat([p.reshape(-1) for p in planes_list])
+        flat = self.torch.cat([p.reshape(-1) for p in tensors])
         dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=group)
         out, o = [], 0
-        for p in planes_list:
+        for p in tensors:
             out.append(flat[o:o + p.numel()].reshape(p.shape))
             o += p.numel()
         return out
 
-    def finalize(self, planes):
+    def send(self, plane, dst, group):
+        import torch.distributed as dist
+        dist.send(plane.contiguous(), dst=dst, group=group)
+
+    def recv(self, shape, src, group):
+        import torch.distributed as dist
+        t = self.torch.empty(shape, dtype=self.torch.float64, device=self.device)
+        dist.recv(t, src=src, group=group)
+        return t
+
+    def finalize_device(self, planes):
+        """plane = numerator / denominator (reference :222), staying on the device"""
         plane = self.torch.empty_like(planes[0])
         self._lib.stitch_finalize(planes[0].data_ptr(), planes[1].data_ptr(), plane.data_ptr(), plane.numel(),
                                   self.torch.cuda.current_stream(self.device).cuda_stream)
-        return plane.cpu().numpy()
+        return plane
+
+    def finalize(self, planes):
+        return self.finalize_device(planes).cpu().numpy()
+
+    def crop(self, tile, shift, tile_relative_size):
+        """``get_tile`` (periodic crop, expansion factor 1) of a device tile, as float64"""
+        n = tile.shape[0]
+        side = int(n * tile_relative_size)
+        rows = (int(n * shift[0]) + self.torch.arange(side, device=self.device)) % tile.shape[0]
+        cols = (int(n * shift[1]) + self.torch.arange(side, device=self.device)) % tile.shape[1]
+        return tile[rows][:, cols].to(self.torch.float64)
 
     def to_host(self, t):
-        return t.cpu().numpy()
+        return t.cpu().numpy() if isinstance(t, self.torch.Tensor) else np.asarray(t)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -247,6 +304,161 @@ def _zoom(tile, n_pixel_tile, mode):
 # ---------------------------------------------------------------------------------------------------
 # process_SLICS
 # ---------------------------------------------------------------------------------------------------
+def plan_planes(costs, world_size):
+    """Owner rank of every plane: longest-processing-time-first list scheduling of the per-plane costs (tiles to
+    paint: 1 for a mass plane, n^2 for a tiled delta plane -- 1, 1, 4, 9, ..., 144 for a SLICS line of sight,
+    reference process_SLICS.py:177-220).  Deterministic: ties go to the lower rank / lower plane index."""
+    owner, load = [0] * len(costs), [0.0] * max(1, world_size)
+    for i in sorted(range(len(costs)), key=lambda k: (-costs[k], k)):
+        r = min(range(len(load)), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
+
+
+def _plane_geometry(delta_size_i, tile_size, n_pixel_tile):
+    """(kind, tiles per side, pixels per side of the painted plane) of one lightcone slice (reference :149, :191-194)."""
+    if delta_size_i < tile_size:
+        return "mass", 1, int(n_pixel_tile * (delta_size_i / tile_size))
+    n_pixel_plane = int(delta_size_i / tile_size * n_pixel_tile)
+    origins, _ = generate_tiling(n_pixel_plane=n_pixel_plane, n_pixel_tile=n_pixel_tile, min_tile_overlap=0.5)
+    return "delta", len(origins), n_pixel_plane
+
+
+class _PlaneFeed:
+    """Produces this rank's planes one ahead of the painter: while plane k is being painted, a worker thread reads
+    plane k+1 (file or ``plane_source``) and hands it to ``backend.stage`` (page-locked buffer + asynchronous upload
+    on a side stream for the device backend) -- the reference reads each file synchronously before touching it
+    (process_SLICS.py:157-159, :187-189)."""
+
+    def __init__(self, indices, load):
+        import threading
+        self._idx, self._load = list(indices), load
+        self._slots = {}
+        self._lock = threading.Condition()
+        self._next = 0
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        for k, i in enumerate(self._idx):
+            with self._lock:
+                while k > self._next + 1:                    # at most one plane ahead of the consumer
+                    self._lock.wait()
+            try:
+                item = ("ok", self._load(i))
+            except BaseException as e:                       # surfaced in get()
+                item = ("err", e)
+            with self._lock:
+                self._slots[i] = item
+                self._lock.notify_all()
+
+    def get(self, i):
+        with self._lock:
+            while i not in self._slots:
+                self._lock.wait()
+            kind, val = self._slots.pop(i)
+            self._next += 1
+            self._lock.notify_all()
+        if kind == "err":
+            raise val
+        return val
+
+
+def _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_slice, shift, SLICS_density, batch, say,
+                 tile_filter=None):
+    """One lightcone slice -> its painted plane (backend array: device tensor / numpy, float64).  Mass-plane branch
+    (reference :149-176): one tile, expanded crop, painted, cropped back.  Delta branch (:177-220): tiled, painted in
+    batches, blended with the Gaussian-edge weights.  ``tile_filter(j, k)``: paint only those tiles (partial planes)."""
+    if delta_size[i] < tile_size:
+        say("  Extracting tile.")
+        if hasattr(be, "extract_tiles") and not SLICS_density:
+            tile = be.extract_tiles(plane, [shift], delta_size[i] / MASSPLANE_SIZE, n_pixel_tile, "mirror",
+                                    expansion_factor=tile_size / delta_size[i])
+        else:
+            plane = be.to_host(plane)
+            tile = get_tile(plane, shift=shift, tile_relative_size=delta_size[i] / MASSPLANE_SIZE,
+                            expansion_factor=tile_size / delta_size[i])
+            if SLICS_density:
+                tile = tile - tile.min()
+            tile = _zoom(tile, n_pixel_tile, "mirror")[None]
+        say("  Painting on tile.")
+        painted = be.paint(painter, tile, z_slice[i], batch)
+        c = (1 - delta_size[i] / tile_size) / 2
+        return be.crop(painted[0], shift=(c, c), tile_relative_size=delta_size[i] / tile_size), None
+    n_pixel_plane = int(delta_size[i] / tile_size * n_pixel_tile)
+    origins, slices = generate_tiling(n_pixel_plane=n_pixel_plane, n_pixel_tile=n_pixel_tile, min_tile_overlap=0.5)
+    say(f"  Using {len(origins)} tiles (on each side)")
+    planes = be.new_planes(n_pixel_plane)
+    on_device = hasattr(be, "extract_tiles")      # crop + cubic-spline zoom on the GPU (SURVEY section 8 f1)
+    tiles, shifts, dest = [], [], []
+    for j, xs in enumerate(origins):
+        for k, ys in enumerate(origins):
+            if tile_filter is not None and not tile_filter(j, k):
+                continue
+            if on_device:
+                shifts.append((xs, ys))
+            else:
+                tile = get_tile(be.to_host(plane), shift=(xs, ys), tile_relative_size=tile_size / delta_size[i])
+                tiles.append(_zoom(tile, n_pixel_tile, "reflect"))
+            dest.append((slices[j][k][0].start, slices[j][k][1].start))
+            say(f"    Painting on tile {j + 1}-{k + 1}")
+    if dest:
+        if on_device:
+            tiles = be.extract_tiles(plane, shifts, tile_size / delta_size[i], n_pixel_tile, "reflect")
+        else:
+            tiles = np.stack(tiles).astype(np.float32, copy=False)
+        painted = be.paint(painter, tiles, z_slice[i], batch)
+        be.accumulate(planes, painted, dest, 0.05, 0.5)
+    return None, planes
+
+
+def _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, delta_path, massplane_path, shifts_path,
+                   z_slice, verbose, SLICS_density, regularise_std, plane_source, rank, world_size, batch, backend,
+                   on_plane):
+    """Shared driver of ``process_SLICS`` and ``paint_lightcone``: planes are dealt to the ranks whole (``plan_planes``),
+    every rank loads ONLY its planes (one ahead, ``_PlaneFeed``), paints and stitches them on its device and calls
+    ``on_plane(i, plane)`` with each finished float64 plane.  No collective in here."""
+    if len(z_SLICS) != len(z_slice):
+        raise ValueError("Shapes of z_SLICS and z_slice need to match!")
+    if regularise_std is not None:
+        # the reference branch is broken (undefined name, SURVEY.md App. E Q3); refuse instead of guessing
+        raise NotImplementedError("regularise_std is not supported (the reference branch raises NameError)")
+    be = backend if backend is not None else DeviceBackend(getattr(painter, "compute_device", None))
+    say = print if (verbose and rank == 0) else (lambda *a, **k: None)
+    geom = [_plane_geometry(delta_size[i], tile_size, n_pixel_tile) for i in range(len(z_SLICS))]
+    owner = plan_planes([g[1] ** 2 for g in geom], world_size)
+    mine = [i for i in range(len(z_SLICS)) if owner[i] == rank]
+    file_shifts = None
+
+    def load(i):
+        kind = geom[i][0]
+        if plane_source is not None:
+            return be.stage(plane_source(i, kind)) if hasattr(be, "stage") else plane_source(i, kind)
+        if kind == "mass":
+            return _load_massplane(massplane_path, z_SLICS[i], i, LOS, be if not SLICS_density else None)[1]
+        return _load_delta(delta_path, z_SLICS[i], LOS, SLICS_density, be)[1]
+
+    feed = _PlaneFeed(mine, load)
+    for i in mine:
+        say(f"Processing z={z_SLICS[i]:.3f}")
+        plane = feed.get(i)
+        shift = None
+        if geom[i][0] == "mass":
+            say("  Tile bigger than delta plane, using mass planes.")
+            if plane_source is not None:
+                shift = np.asarray(shifts_path)[i]
+            else:
+                if file_shifts is None:
+                    file_shifts = np.loadtxt(os.path.join(shifts_path, f"random_shift_LOS{LOS}"))[::-1]
+                shift = file_shifts[i]
+        cropped, planes = _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_slice, shift,
+                                       SLICS_density, batch, say)
+        on_plane(i, cropped if planes is None else be.finalize_device(planes))
+        del plane
+    return be, owner, geom
+
+
 def process_SLICS(painter,
                   tile_size, n_pixel_tile,
                   LOS, z_SLICS, delta_size, delta_path, massplane_path, shifts_path,
@@ -262,101 +474,71 @@ def process_SLICS(painter,
 
     ``plane_source(i, kind)`` with ``kind`` in ``{"mass", "delta"}``, when given, returns the (already rescaled)
     plane ``i`` as an array instead of reading the SLICS files, and ``shifts_path`` may then be an array of
-    per-plane ``(x, y)`` shifts."""
-    if len(z_SLICS) != len(z_slice):
-        raise ValueError("Shapes of z_SLICS and z_slice need to match!")
-    if regularise_std is not None:
-        # the reference branch is broken (undefined name, SURVEY.md App. E Q3); refuse instead of guessing
-        raise NotImplementedError("regularise_std is not supported (the reference branch raises NameError)")
-    be = backend if backend is not None else DeviceBackend(getattr(painter, "compute_device", None))
-    say = print if (verbose and rank == 0) else (lambda *a, **k: None)
+    per-plane ``(x, y)`` shifts.
 
-    results = []          # per plane: ("mass", device tile or None, crop args) | ("delta", planes tensor)
-    item = 0              # global work-item counter: item % world_size == rank paints it
-    for i in range(len(z_SLICS)):
-        say(f"Processing z={z_SLICS[i]:.3f}")
-        if delta_size[i] < tile_size:
-            say("  Tile bigger than delta plane, using mass planes.")
-            mine = (item % world_size) == rank
-            item += 1
-            painted = None
-            if mine:
-                if plane_source is not None:
-                    plane = plane_source(i, "mass")
-                    shift = np.asarray(shifts_path)[i]
-                else:
-                    shifts = np.loadtxt(os.path.join(shifts_path, f"random_shift_LOS{LOS}"))[::-1]
-                    fn, plane = _load_massplane(massplane_path, z_SLICS[i], i, LOS, be if not SLICS_density else None)
-                    say(f"  Loading {fn}.")
-                    shift = shifts[i]
-                say("  Extracting tile.")
-                if hasattr(be, "extract_tiles") and not SLICS_density:
-                    tile = be.extract_tiles(plane, [shift], delta_size[i] / MASSPLANE_SIZE, n_pixel_tile, "mirror",
-                                            expansion_factor=tile_size / delta_size[i])
-                else:
-                    tile = get_tile(plane, shift=shift, tile_relative_size=delta_size[i] / MASSPLANE_SIZE,
-                                    expansion_factor=tile_size / delta_size[i])
-                    if SLICS_density:
-                        tile = tile - tile.min()
-                    tile = _zoom(tile, n_pixel_tile, "mirror")[None]
-                say("  Painting on tile.")
-                painted = be.to_host(be.paint(painter, tile, z_slice[i], batch))[0]
-                c = (1 - delta_size[i] / tile_size) / 2
-                painted = get_tile(painted, shift=(c, c), tile_relative_size=delta_size[i] / tile_size)
-            results.append(("mass", painted))
-            continue
-        if plane_source is not None:
-            delta = plane_source(i, "delta")
-        else:
-            fn, delta = _load_delta(delta_path, z_SLICS[i], LOS, SLICS_density, be)
-        n_pixel_plane = int(delta_size[i] / tile_size * n_pixel_tile)
-        origins, slices = generate_tiling(n_pixel_plane=n_pixel_plane, n_pixel_tile=n_pixel_tile, min_tile_overlap=0.5)
-        say(f"  Using {len(origins)} tiles (on each side)")
-        planes = be.new_planes(n_pixel_plane)
-        on_device = hasattr(be, "extract_tiles")      # crop + cubic-spline zoom on the GPU (SURVEY section 8 f1)
-        tiles, shifts, dest = [], [], []
-        for j, xs in enumerate(origins):
-            for k, ys in enumerate(origins):
-                mine = (item % world_size) == rank
-                item += 1
-                if not mine:
-                    continue
-                if on_device:
-                    shifts.append((xs, ys))
-                else:
-                    tile = get_tile(delta, shift=(xs, ys), tile_relative_size=tile_size / delta_size[i])
-                    tiles.append(_zoom(tile, n_pixel_tile, "reflect"))
-                dest.append((slices[j][k][0].start, slices[j][k][1].start))
-                say(f"    Painting on tile {j + 1}-{k + 1}")
-        if dest:
-            if on_device:
-                tiles = be.extract_tiles(delta, shifts, tile_size / delta_size[i], n_pixel_tile, "reflect")
-            else:
-                tiles = np.stack(tiles).astype(np.float32, copy=False)
-            painted = be.paint(painter, tiles, z_slice[i], batch)
-            be.accumulate(planes, painted, dest, 0.05, 0.5)
-        results.append(("delta", planes))
-
-    # ---- assemble: one reduce of all partial planes, then plane = numerator / denominator
-    delta_idx = [i for i, r in enumerate(results) if r[0] == "delta"]
+    Sharding (``world_size > 1``): whole planes are dealt to the ranks by cost (``plan_planes``); a rank reads, paints
+    and stitches only its own planes; afterwards every finished plane is sent to rank 0 point to point.  Callers
+    that want the Compton-y map rather than the planes should use ``paint_lightcone``: it projects on the owning
+    rank and moves one map instead of every plane."""
+    done = {}
+    be, owner, geom = _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, delta_path,
+                                     massplane_path, shifts_path, z_slice, verbose, SLICS_density, regularise_std,
+                                     plane_source, rank, world_size, batch, backend, lambda i, p: done.__setitem__(i, p))
     if world_size > 1:
-        import torch.distributed as dist
-        if delta_idx:
-            reduced = be.reduce([results[i][1] for i in delta_idx], 0, group)
-            for i, p in zip(delta_idx, reduced):
-                results[i] = ("delta", p)
-        mass = [None] * world_size
-        dist.gather_object([(i, r[1]) for i, r in enumerate(results) if r[0] == "mass" and r[1] is not None],
-                           mass if rank == 0 else None, dst=0, group=group)
+        for i in range(len(z_SLICS)):                       # plane i: owner -> rank 0, same order on every rank
+            if owner[i] == 0:
+                continue
+            if rank == owner[i]:
+                be.send(done.pop(i), 0, group)
+            elif rank == 0:
+                done[i] = be.recv((geom[i][2], geom[i][2]), owner[i], group)
         if rank != 0:
             return (None, []) if return_problematic_tiles else None
-        for part in mass:
-            for i, p in part:
-                results[i] = ("mass", p)
-    painted_planes = [be.finalize(r[1]) if r[0] == "delta" else np.asarray(r[1], np.float64) for r in results]
+    painted_planes = [np.asarray(be.to_host(done[i]), np.float64) for i in range(len(z_SLICS))]
     if return_problematic_tiles:
         return painted_planes, []
     return painted_planes
+
+
+def paint_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, delta_path, massplane_path, shifts_path,
+                    z_slice, resolution, map_size, cosmo, order=5, verbose=True, SLICS_density=False, plane_source=None,
+                    rank=0, world_size=1, group=None, batch=64, backend=None, drop_planes=None, keep_planes=False):
+    """``process_SLICS`` + ``create_y_map`` (reference scripts/create_lightcone.py:106-128) as one sharded pass:
+    every rank paints and stitches its own planes and adds each, with the plane's physical prefactor, to ITS partial
+    Compton-y map on its device (the projection is linear in the planes); ONE reduction of the ``resolution``^2
+    float64 map (19 MB at 1549^2, NCCL over NVLink on a GPU box) assembles the result on rank 0 -- no painted plane
+    ever leaves the GPU that made it.  Returns ``y_map`` on rank 0 (None elsewhere); with ``drop_planes=n`` a pair
+    ``(y_map, y_map_without_the_first_n_planes)``; ``keep_planes=True`` adds the rank's own planes (dict index ->
+    host array) as the last element."""
+    n = len(z_SLICS)
+    sizes = [_plane_geometry(delta_size[i], tile_size, n_pixel_tile)[2] for i in range(n)]
+    fac = y_map_factors(z_SLICS, resolution, map_size, cosmo, sizes)
+    fac_drop = y_map_factors(z_SLICS[drop_planes:], resolution, map_size, cosmo, sizes[drop_planes:]) \
+        if drop_planes is not None else None
+    be = backend if backend is not None else DeviceBackend(getattr(painter, "compute_device", None))
+    maps = [be.new_map(resolution)] + ([be.new_map(resolution)] if drop_planes is not None else [])
+    kept = {}
+
+    def on_plane(i, plane):
+        if verbose and rank == 0:
+            print(f"z : {z_SLICS[i]:0.3f}, plane shape: {tuple(plane.shape)}, zoom_factor: {resolution / plane.shape[0]:0.3f}")
+        be.zoom_accumulate(maps[0], plane, fac[i], order)
+        if drop_planes is not None and i >= drop_planes:
+            be.zoom_accumulate(maps[1], plane, fac_drop[i - drop_planes], order)
+        if keep_planes:
+            kept[i] = np.asarray(be.to_host(plane), np.float64)
+
+    _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, delta_path, massplane_path, shifts_path,
+                   z_slice, verbose, SLICS_density, None, plane_source, rank, world_size, batch, be, on_plane)
+    if world_size > 1:
+        maps = be.reduce(maps, 0, group)                    # the one collective of the run
+    out = None
+    if rank == 0:
+        out = tuple(np.asarray(be.to_host(m), np.float64) for m in maps)
+        out = out[0] if drop_planes is None else out
+    if keep_planes:
+        return (out, kept) if drop_planes is None else (*(out or (None, None)), kept)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -390,12 +572,10 @@ def _cosmo_funcs(cosmo):
             lambda chi: ccl.scale_factor_of_chi(cosmo, chi))
 
 
-def create_y_map(painted_planes, z, resolution, map_size, cosmo, order=3, verbose=True, backend=None):
-    """Project painted pressure planes to a Compton-y map (reference :12-66): per plane NaN -> 0, physical
-    prefactor, spline zoom to ``resolution`` (mode ``mirror``), sum.  ``backend``: a ``DeviceBackend`` runs the
-    zoom-and-accumulate on the GPU (orders 3 and 5; csrc/bp_zoom.cu), default: host scipy as the reference."""
+def y_map_factors(z, resolution, map_size, cosmo, plane_sizes):
+    """Per-plane prefactor of the Compton-y projection (reference :14-62): cell volume, electron / ion number
+    ratios, sigma_T / m_e c^2, the slab's mean pixel area and the flux-conserving 1 / zoom^2."""
     import scipy.integrate
-    import scipy.ndimage
     h, dist_of_a, a_of_chi = _cosmo_funcs(cosmo)
     slab = 252.5 / h
     d_A = np.array(dist_of_a(1 / (1 + np.array(z))), float) - slab / 2
@@ -413,13 +593,22 @@ def create_y_map(painted_planes, z, resolution, map_size, cosmo, order=3, verbos
     Xe, Xi = 1.17, 1.08
     V_c = (400 / h / 2048 * mpc / cm) ** 3                     # cell volume in cm^3
     y_fac = 8.125561e-16 * eV * mpc ** -2                      # sigma_T / m_e c^2 in Mpc^2 eV^-1
+    return [V_c * (Xe + Xi) / Xe * y_fac / A_pix_eff[i] / (resolution / plane_sizes[i]) ** 2 for i in range(len(z))]
+
+
+def create_y_map(painted_planes, z, resolution, map_size, cosmo, order=3, verbose=True, backend=None):
+    """Project painted pressure planes to a Compton-y map (reference :12-66): per plane NaN -> 0, physical
+    prefactor, spline zoom to ``resolution`` (mode ``mirror``), sum.  ``backend``: a ``DeviceBackend`` runs the
+    zoom-and-accumulate on the GPU (orders 3 and 5; csrc/bp_zoom.cu), default: host scipy as the reference."""
+    import scipy.ndimage
+    facs = y_map_factors(z, resolution, map_size, cosmo, [p.shape[0] for p in painted_planes])
     on_device = backend is not None and hasattr(backend, "zoom_accumulate") and order in (3, 5) and \
         all(p.ndim == 2 and p.shape[0] == p.shape[1] and int(round(p.shape[0] * (resolution / p.shape[0]))) == resolution
             for p in painted_planes)
     y_map = backend.new_map(resolution) if on_device else np.zeros((resolution, resolution))
     for i, plane in enumerate(painted_planes):
         zoom_factor = resolution / plane.shape[0]
-        fac = V_c * (Xe + Xi) / Xe * y_fac / A_pix_eff[i] / zoom_factor ** 2
+        fac = facs[i]
         if verbose:
             print(f"z : {z[i]:0.3f}, plane shape: {plane.shape}, zoom_factor: {zoom_factor:0.3f}")
         if on_device:

@@ -4,7 +4,8 @@
 
 Run on a B200.  Net creation normally looks each layer up in the shipped table (deterministic); here
 ``bp_tuning_mode(1)`` makes it time the candidates on a full chunk instead and record the winners for the
-production shapes: the fiducial CVAE (512^2, 256-tile chunk) and the CGAN generator, fp16 and bf16.  The
+production shapes: the fiducial CVAE (512^2, 256-tile chunk) and the CGAN generator; fp16, bf16 and the
+split-precision fp32 path.  The
 result is data to commit, so that every process afterwards paints bit-identical tiles.
 """
 import argparse
@@ -17,7 +18,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=_lib.TUNING_TABLE)
     ap.add_argument("--log", action="store_true")
-    ap.add_argument("--formats", default="fp16,bf16")
+    ap.add_argument("--formats", default="fp16,bf16,fp32")
     ap.add_argument("--no-cgan", action="store_true")
     args = ap.parse_args()
     from .painter import CGANPainter, CVAEPainter

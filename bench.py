@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=256, help="tiles in the bounded cpu_baseline sample (about 10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed batch")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the secondary fp32-accurate measurement")
     ap.add_argument("--profile-layers", action="store_true", help="print the per-layer timing table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -331,6 +332,43 @@ def main():
                     name, li, info["kernel"], info["stride"], info["cin"], info["cout"], info["H"], info["W"],
                     info["tensor"], t_ms, 100 * t_ms / tot, tf), file=sys.stderr)
 
+    # ---- second driver-visible number: the fp32-accurate tensor-core path (BASELINE configs[1]: "bf16 and fp32") on
+    # the same 256 tiles, device-resident, with its own parity check at north_star's fp32 tolerance
+    fp32 = None
+    if rank == 0 and world == 1 and not args.no_fp32 and args.precision != "fp32":
+        p32 = CVAEPainter.synthetic(tile_size=TILE, seed=0, compute_device="cuda:%d" % local, precision="fp32", max_batch=n)
+        net32 = p32.model.net
+        d_out32 = torch.empty_like(d_out)
+
+        def step32():
+            net32.cvae_paint_device(d_tiles.data_ptr(), d_eps.data_ptr(), _lib.BP_LATENT_EPS, 0, tparams, flags,
+                                    d_out32.data_ptr(), n, stream)
+        for _ in range(3):
+            step32()
+        torch.cuda.synchronize()
+        k32 = max(3, min(args.steps, 5))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(k32):
+            step32()
+        f1.record()
+        torch.cuda.synchronize()
+        ms32 = f0.elapsed_time(f1) / k32
+        errs32 = []
+        if not args.no_parity:
+            for i in sorted(set(int(v) for v in np.linspace(0, n - 1, min(n, 4)))):
+                ref = orc.paint(tiles_h[i], 0.0, stats, eps=eps_h[i:i + 1]).astype(np.float64)
+                got = d_out32[i].cpu().numpy().astype(np.float64)
+                errs32.append(float(np.sqrt(((got - ref) ** 2).sum() / (ref ** 2).sum())))
+        fp32 = {"value": n / (ms32 * 1e-3), "unit": "tiles/s", "ms_per_step": ms32, "steps": k32,
+                "dtype": "f32-accurate: fp16 (hi, lo) split operands on tcgen05, fp32 accumulation",
+                "frac_of_bf16_roofline": n / (ms32 * 1e-3) * FLOPS_PER_TILE / 1e12 / peaks()["bf16_tflops"],
+                "parity": {"tiles": len(errs32), "max_rel_l2": max(errs32) if errs32 else None, "tol": 1e-4,
+                           "ok": bool(errs32 and max(errs32) <= 1e-4)} if errs32 else None}
+        if errs32 and max(errs32) > 1e-4:
+            raise RuntimeError("fp32 parity of the benchmarked batch failed: %r" % (fp32,))
+        del p32, net32
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt = cpu_baseline(args.cpu_tiles, os.cpu_count())
@@ -342,11 +380,12 @@ def main():
             "metric": "tiles/sec painted (fiducial CVAE)", "value": total_tiles / (ms * 1e-3), "unit": "tiles/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}.get(args.precision, args.precision), "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32 (fp16 hi/lo split operands)", "fp32-ffma": "f32"}.get(args.precision, args.precision),
+            "data": "synthetic",
             "config": workload_config(n, world),
             "e2e": {"value": total_tiles / (e2e_ms * 1e-3), "unit": "tiles/s",
                     "h2d_bytes_per_step": int(tiles_h.nbytes + eps_h.nbytes), "d2h_bytes_per_step": int(out_h.nbytes)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "fp32": fp32}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

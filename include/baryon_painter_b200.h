@@ -58,10 +58,14 @@ enum { BP_RES_NONE = 0, BP_RES_OPEN = 1, BP_RES_CLOSE = 2 };
 
 /* arithmetic of the convolution stacks */
 enum {
-  BP_PREC_F32 = 0,   /* fp32 FFMA kernels; <= 1e-4 rel-L2 per tile vs the reference                  */
-  BP_PREC_BF16 = 1,  /* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma .kind::f16)            */
-  BP_PREC_F16 = 2    /* fp16 operands, same kernel and rate; 8x finer rounding than bf16 -- the
-                        16-bit path that holds <= 1e-2 rel-L2 through the exp(4x) inverse transform */
+  BP_PREC_F32 = 0,   /* fp32-accurate on the tensor cores: every activation and weight travels as two fp16
+                        numbers (hi = fp16(v), lo = fp16(v - hi): 22 significant bits), each product is
+                        x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in fp32 in TMEM; <= 1e-4 rel-L2 per tile
+                        vs the reference's fp32 torch.nn.Conv2d (reference models/utils.py:128-131)        */
+  BP_PREC_BF16 = 1,  /* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma .kind::f16)                   */
+  BP_PREC_F16 = 2,   /* fp16 operands, same kernel and rate; 8x finer rounding than bf16 -- the
+                        16-bit path that holds <= 1e-2 rel-L2 through the exp(4x) inverse transform        */
+  BP_PREC_F32_FFMA = 3 /* scalar fp32 FFMA kernels (no tensor cores): the on-device cross-check of the others */
 };
 
 /* how the CVAE latent is obtained (reference cvae.py:63-66, 97-100, 149-155) */

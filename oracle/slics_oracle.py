@@ -48,6 +48,33 @@ class NumpyBackend:
     def finalize(self, planes):
         return planes[0] / planes[1]
 
+    finalize_device = finalize
+
+    def crop(self, tile, shift, tile_relative_size):
+        from baryon_painter_b200.process_SLICS import get_tile
+        return get_tile(np.asarray(tile), shift=shift, tile_relative_size=tile_relative_size)
+
+    def send(self, plane, dst, group):
+        import torch
+        import torch.distributed as dist
+        dist.send(torch.from_numpy(np.ascontiguousarray(plane, np.float64)), dst=dst, group=group)
+
+    def recv(self, shape, src, group):
+        import torch
+        import torch.distributed as dist
+        t = torch.empty(shape, dtype=torch.float64)
+        dist.recv(t, src=src, group=group)
+        return t.numpy()
+
+    def new_map(self, resolution):
+        return np.zeros((resolution, resolution))
+
+    def zoom_accumulate(self, y_map, plane, scale, order):
+        import scipy.ndimage
+        plane = np.asarray(plane, np.float64)
+        d = np.where(np.isnan(plane), 0.0, plane) * scale
+        y_map += scipy.ndimage.zoom(d, zoom=y_map.shape[0] / plane.shape[0], order=order, mode="mirror")
+
     def to_host(self, t):
         return np.asarray(t)
 

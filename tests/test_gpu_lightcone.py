@@ -83,3 +83,32 @@ def test_tile_loop_vs_oracle(precision, tol):
         y_host = ps.create_y_map(dev, [0.21, 0.52], 64, 10.0, cosmo, order=order, verbose=False)
         y_dev = ps.create_y_map(dev, [0.21, 0.52], 64, 10.0, cosmo, order=order, verbose=False, backend=ps.DeviceBackend("cuda:0"))
         assert rel_l2(y_dev, y_host) <= 1e-10
+
+
+def test_paint_lightcone_device_equals_two_step():
+    """paint_lightcone (planes stay on the device, projected there, quintic spline) against
+    create_y_map(process_SLICS(...)) of the same painter; and a second run re-using the backend with fresh numpy
+    planes of the same shape (a stale uploaded plane must never be matched by address)."""
+    from baryon_painter_b200 import process_SLICS as ps
+    from baryon_painter_b200.painter import CVAEPainter
+    import scipy.ndimage
+    tile = 64
+    rng = np.random.default_rng(11)
+
+    def field(n):
+        g = scipy.ndimage.gaussian_filter(rng.standard_normal((n, n)), 4.0, mode="wrap")
+        return np.exp(g / g.std() - 0.5).astype(np.float32)
+
+    painter = _FixedEps(CVAEPainter.synthetic(tile_size=tile, seed=4, precision="fp16", max_batch=16))
+    be = ps.DeviceBackend("cuda:0")
+    cosmo = ps.FlatLCDM()
+    for trial in range(2):
+        planes_in = [field(300), field(400), field(400)]
+        args = dict(tile_size=100.0, n_pixel_tile=tile, LOS=1, z_SLICS=[0.1, 0.2, 0.5], delta_size=[60.0, 150.0, 230.0],
+                    delta_path=None, massplane_path=None, shifts_path=rng.random((3, 2)), z_slice=[0.11, 0.21, 0.52],
+                    plane_source=lambda i, kind: np.array(planes_in[i]))      # a fresh array on every call
+        planes = ps.process_SLICS(painter, batch=16, verbose=False, backend=be, **args)
+        ref = ps.create_y_map(planes, args["z_SLICS"], 80, 10.0, cosmo, order=5, verbose=False)
+        y = ps.paint_lightcone(painter, resolution=80, map_size=10.0, cosmo=cosmo, order=5, verbose=False, batch=16,
+                               backend=be, **args)
+        assert y.shape == (80, 80) and rel_l2(y, ref) <= 1e-9, (trial, rel_l2(y, ref))

@@ -101,8 +101,68 @@ def _rank_main(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_plan_planes_lpt():
+    """planes are dealt whole, by cost, longest first (a SLICS line of sight: 1, 1, 4, 9, ..., 144 tiles per plane)"""
+    costs = [1, 1, 4, 9, 9, 16, 25, 36, 49, 64, 81, 100, 121, 121, 144]
+    assert ps.plan_planes(costs, 1) == [0] * 15
+    for w in (2, 4, 8):
+        owner = ps.plan_planes(costs, w)
+        load = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(w)]
+        assert sum(load) == 781 and max(load) <= max(144, 781 / w * 1.08)       # LPT: within a few % of the bound
+        assert owner == ps.plan_planes(costs, w)                                   # deterministic
+    assert max(sum(c for c, o in zip(costs, ps.plan_planes(costs, 8)) if o == r) for r in range(8)) == 144
+
+
+def _lightcone_rank_main(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import slics_oracle as so
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g, args = _case()
+    args = {k: v for k, v in args.items() if k != "verbose"}
+    res = ps.paint_lightcone(so.StubPainter(), resolution=48, map_size=10.0, cosmo=ps.FlatLCDM(), order=3, verbose=False,
+                             backend=so.NumpyBackend(), rank=rank, world_size=world, drop_planes=1, **args)
+    if rank == 0:
+        q.put([np.asarray(m) for m in res])
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_paint_lightcone_sharded_gloo():
+    """the fused path: every rank paints its planes and projects them into its partial y map; ONE reduce of the map.
+    Equals create_y_map(process_SLICS(...)) of the unsharded run (also with the first plane dropped)."""
+    import torch.multiprocessing as mp
+    from oracle import slics_oracle as so
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_lightcone_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    y_map, y_drop = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g, args = _case()
+    planes = ps.process_SLICS(so.StubPainter(), backend=so.NumpyBackend(), **args)
+    z = args["z_SLICS"]
+    ref = ps.create_y_map(planes, z, 48, 10.0, ps.FlatLCDM(), order=3, verbose=False)
+    ref_drop = ps.create_y_map(planes[1:], z[1:], 48, 10.0, ps.FlatLCDM(), order=3, verbose=False)
+    assert np.allclose(y_map, ref, rtol=1e-12, atol=0) and np.allclose(y_drop, ref_drop, rtol=1e-12, atol=0)
+    # single process, same call
+    one = ps.paint_lightcone(so.StubPainter(), resolution=48, map_size=10.0, cosmo=ps.FlatLCDM(), order=3, verbose=False,
+                             backend=so.NumpyBackend(), **{k: v for k, v in args.items() if k != "verbose"})
+    assert np.allclose(one, ref, rtol=1e-12, atol=0)
+
+
 def test_process_slics_sharded_gloo():
-    """world_size 2: work items dealt round-robin, one reduce at the end; rank 0 holds the assembled planes"""
+    """world_size 2: whole planes dealt by cost, each rank paints only its own, finished planes sent to rank 0"""
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

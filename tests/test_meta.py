@@ -99,3 +99,40 @@ def test_transforms_agree_with_oracle_restatement():
         back = ti(t(x, field="dm", z=z), field="dm", z=z)
         assert np.allclose(back, x, atol=2e-5 * sig * max(1.0, x.max()))
     assert t.sigma("dm", -3.0) == t.sigma("dm", 0.0) and t.sigma("dm", 9.0) == t.sigma("dm", 2.0)
+
+
+def test_restricted_unpickler_refuses_escape_chains(tmp_path):
+    """a crafted model_meta must not reach os.system through dill's _import_module / _get_attr or
+    builtins.getattr; module names are an exact whitelist ('numpy_evil' does not pass a prefix test)."""
+    import io
+    import pickle
+    import pickletools  # noqa: F401
+    from baryon_painter_b200 import meta
+
+    def stream(ops):
+        return b"\x80\x02" + ops + b"."
+
+    def glob(mod, name):
+        return b"c" + mod.encode() + b"\n" + name.encode() + b"\n"
+
+    def ustr(s):
+        return b"X" + len(s).to_bytes(4, "little") + s.encode()
+
+    # dill._dill._import_module('numpy.lib._npyio_impl')
+    bad1 = stream(glob("dill._dill", "_import_module") + ustr("numpy.lib._npyio_impl") + b"\x85R")
+    # getattr(_import_module('numpy'), 'os')
+    bad2 = stream(glob("builtins", "getattr") + glob("dill._dill", "_import_module") + ustr("numpy") + b"\x85R" +
+                  ustr("os") + b"\x86R")
+    # dill._dill._import_module('numpy_evil')
+    bad3 = stream(glob("dill._dill", "_import_module") + ustr("numpy_evil") + b"\x85R")
+    # getattr on a real object (a dict)
+    bad4 = stream(glob("builtins", "getattr") + b"}" + ustr("get") + b"\x86R")
+    # a global outside the whitelist
+    bad5 = stream(glob("os", "system") + ustr("true") + b"\x85R")
+    for blob in (bad1, bad2, bad3, bad4, bad5):
+        with pytest.raises(pickle.UnpicklingError):
+            meta._MetaUnpickler(io.BytesIO(blob)).load()
+    # the whitelisted numpy reconstructors still resolve through the same doors
+    ok = stream(glob("builtins", "getattr") + glob("dill._dill", "_import_module") + ustr("numpy") + b"\x85R" +
+                ustr("dtype") + b"\x86R")
+    assert meta._MetaUnpickler(io.BytesIO(ok)).load() is np.dtype
