@@ -124,5 +124,7 @@ int launch_welford(const float* x, double* mean, double* m2, int count, size_t n
 int launch_var_finalize(const double* mean, const double* m2, float* mean_out, float* var_out, int count, size_t n,
                         cudaStream_t s);
 int launch_rng_normal(float* out, uint64_t seed, uint64_t offset, size_t n, cudaStream_t s);
+int launch_kl_sum(const float* q, const float* prior, int nb, int hw, double* dst, cudaStream_t s);
+int launch_sqdiff_sum(const float* a, const float* b, size_t n, double* dst, cudaStream_t s);
 
 }  // namespace bp

@@ -388,6 +388,54 @@ int launch_sample_z(const float* prior_out, const float* eps, float* latent, flo
 }
 
 // ------------------------------------------------------------------------------------------
+// evidence lower bound pieces (reference cvae.py:122-147): float64 block reductions + one atomic per block
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum_to(double v, double* dst) {
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if (threadIdx.x == 0) atomicAdd(dst, v);
+  }
+}
+// sum over (n, p) of (pm - zm)^2 / pv + exp(zlv) / pv + plv - zlv - 1, with (zm, zlv) = q[n][0/1][p] and
+// (pm, plv) = prior[n][0/1][p], pv = exp(plv)
+__global__ void kl_sum_kernel(const float* __restrict__ q, const float* __restrict__ prior, int nb, int hw, double* dst) {
+  double acc = 0.0;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nb * hw; g += gridDim.x * blockDim.x) {
+    const int n = g / hw, p = g - n * hw;
+    const float zm = q[(size_t)n * 2 * hw + p], zlv = q[(size_t)n * 2 * hw + hw + p];
+    const float pm = prior[(size_t)n * 2 * hw + p], plv = prior[(size_t)n * 2 * hw + hw + p];
+    const float pv = expf(plv);
+    acc += (double)((pm - zm) * (pm - zm) / pv + expf(zlv) / pv + plv - zlv - 1.f);
+  }
+  block_sum_to(acc, dst);
+}
+__global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* dst) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    acc += (double)(d * d);
+  }
+  block_sum_to(acc, dst);
+}
+int launch_kl_sum(const float* q, const float* prior, int nb, int hw, double* dst, cudaStream_t s) {
+  kl_sum_kernel<<<std::max(1, std::min(148, (nb * hw + 255) / 256)), 256, 0, s>>>(q, prior, nb, hw, dst);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+int launch_sqdiff_sum(const float* a, const float* b, size_t n, double* dst, cudaStream_t s) {
+  sqdiff_sum_kernel<<<(int)std::max<size_t>(1, std::min<size_t>(148 * 8, (n + 255) / 256)), 256, 0, s>>>(a, b, n, dst);
+  launch_counter()++;
+  BP_CUDA_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // running mean / M2 over latent draws (variance maps, BASELINE config 4)
 // ------------------------------------------------------------------------------------------
 // The running moments are float64: painted pressure spans ~6 decades within a tile and the M2 update subtracts

@@ -464,6 +464,15 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
       // of each: the tuning table names the one to build; without an entry the cost model's first that fits is used
       const std::string key = tune_key(*r.l, fmt, net->split ? 1 : 0);
       const void* skip_ptr = op.skip >= 0 ? P.acts[op.skip].ptr : nullptr;
+      // no formulation fits (e.g. a 9x9 convolution over 128-byte split-precision pixels: more k-step slots than the
+      // offset table holds): this one layer runs on the fp32 FFMA kernel instead, bridged by layout conversions
+      auto fallback = [&]() {
+        cudaFree(P.acts[op.out].ptr);
+        net->v2.owned.pop_back();
+        P.acts.pop_back();
+        r.l->v2 = false;
+        r.w = false;
+      };
       TuneEntry te;
       if (tune_lookup(key, &te) && !g_tune_mode) {
         rc = BP_E_UNSUPPORTED;
@@ -487,17 +496,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
         }
         if (rc == BP_E_UNSUPPORTED)
           set_error("no window-GEMM formulation of %s fits:%s", key.c_str(), why.substr(0, 800).c_str());
-        if (rc == BP_E_UNSUPPORTED && d.res == BP_RES_NONE) {
-          // (e.g. a 9x9 convolution over 128-byte split-precision pixels: more k-step slots than the offset table
-          // holds) -- this one layer runs on the fp32 FFMA kernel instead, bridged by layout conversions
-          cudaFree(P.acts[op.out].ptr);
-          net->v2.owned.pop_back();
-          P.acts.pop_back();
-          r.l->v2 = false;
-          r.w = false;
-          --i;
-          continue;
-        }
+        if (rc == BP_E_UNSUPPORTED && d.res == BP_RES_NONE) { fallback(); --i; continue; }
         if (rc != BP_OK) { op.w = nullptr; return rc; }
       }
       if (!op.w) {
@@ -523,6 +522,7 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
           if (!op.w || ms < best_ms) { if (op.w) wconv_free(op.w); op.w = w; best_ms = ms; best_ci = ci; }
           else wconv_free(w);
         }
+        if (rc == BP_E_UNSUPPORTED && !op.w && d.res == BP_RES_NONE) { fallback(); --i; continue; }
         if (rc != BP_OK) { if (op.w) wconv_free(op.w); op.w = nullptr; return rc; }
         for (int rank = 1; rank < max_rank; ++rank) {
           WLayer* w = nullptr;

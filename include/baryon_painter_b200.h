@@ -106,6 +106,12 @@ typedef struct bp_cvae_desc {
   const bp_layer_desc* p_z_in;   /* in: latent (1 ch) -> 1 ch at tile resolution      */
   const bp_layer_desc* p_y_z_in; /* in: [p_z_in(latent), y, z-plane] (3 ch)           */
   const bp_layer_desc* p_mu_out; /* -> 1 ch x_mu                                      */
+  /* recognition network (reference cvae.py:24-26, 68-80); optional (n_* = 0): needed by bp_cvae_elbo_host only */
+  int32_t n_q_x_in, n_q_y_in, n_q_out;
+  const bp_layer_desc* q_x_in;   /* in: x (1 ch)                                      */
+  const bp_layer_desc* q_y_in;   /* in: [y, z-plane] (2 ch)                           */
+  const bp_layer_desc* q_out;    /* in: cat(q_x_in, q_y_in) -> (z_mu, z_log_var)      */
+  float likelihood_scaling;      /* reference cvae.py:56, default 1                   */
 } bp_cvae_desc;
 
 /* per-call elementwise transform parameters (host arrays of length n; sigma computed on
@@ -148,6 +154,19 @@ int bp_cgan_paint_host(bp_net* net, const float* tiles, const bp_transform_param
  * pressure; host pointers (BASELINE config 4; reference: repeated paint() calls) */
 int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transform_params* tp,
                                 int n_draws, uint64_t seed, float* mean_out, float* var_out, int n);
+
+/* replaces CVAE.forward with CVAE.Q (reference cvae.py:68-80, 122-147): the evidence lower bound of a batch of n
+ * (x = pressure, y = dark matter) tile pairs, as CVAEPainter.validate evaluates it (reference painter.py:295-367).
+ *   z ~ Q(x, y): (z_mu, z_log_var) = q_out(cat(q_x_in(x'), q_y_in([y', z]))), z = z_mu + eps*(exp(z_log_var/2) + min_z_var)
+ *   KL_term = 0.5/n * sum((pm - z_mu)^2/pv + exp(z_log_var)/pv + plv - z_log_var - 1) over the prior network's (pm, plv)
+ *   log_likelihood = -0.5 ln(2 pi) - 0.5/n * sum((x' - x_mu(z, y))^2)          (fixed variance, L = 1)
+ *   ELBO = -KL_term + likelihood_scaling * log_likelihood
+ * With BP_FLAG_TRANSFORM x' = ln(x/sigma_out + 1)/k_out - shift_out and y' = ln(y/sigma_in + 1)/k_in - shift_in (the
+ * dataset transforms of reference scripts/CVAE_single_scale.py:34-65); eps as in bp_cvae_paint (BP_LATENT_EPS / _SEED).
+ * Host pointers; stats = {ELBO, KL_term, log_likelihood}; z_mu / z_log_var ([n][h][w], optional) receive Q's output. */
+int bp_cvae_elbo_host(bp_net* net, const float* x_tiles, const float* y_tiles, const float* eps, int latent_mode,
+                      uint64_t seed, const bp_transform_params* tp, int flags, int n, double* stats, float* z_mu,
+                      float* z_log_var);
 
 /* ---- lightcone stitching (reference process_SLICS.py:85-99, 211-220) -------------------- */
 /* plane_num[y0+i][x0+j] += w(i,j)*tile[t][i][j]; plane_den[...] += w(i,j) for every tile t;
