@@ -30,7 +30,7 @@ EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destro
            "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles", "bp_zoom_accumulate", "bp_plane_prepare",
            "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
            "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile", "bp_net_chunk",
-           "bp_tuning_set", "bp_tuning_get", "bp_tuning_mode", "bp_rng_normal_host",
+           "bp_tuning_set", "bp_tuning_get", "bp_tuning_mode", "bp_rng_normal_host", "bp_cvae_elbo_host",
            "bp_last_error", "bp_version")
 
 # which tensor-core formulation / tiling every layer runs with (see include/baryon_painter_b200.h, "formulation table")
@@ -50,7 +50,10 @@ class CvaeDesc(ctypes.Structure):
                 ("n_prior", ctypes.c_int32), ("n_p_z_in", ctypes.c_int32), ("n_p_y_z_in", ctypes.c_int32),
                 ("n_p_mu_out", ctypes.c_int32),
                 ("prior", ctypes.POINTER(LayerDesc)), ("p_z_in", ctypes.POINTER(LayerDesc)),
-                ("p_y_z_in", ctypes.POINTER(LayerDesc)), ("p_mu_out", ctypes.POINTER(LayerDesc))]
+                ("p_y_z_in", ctypes.POINTER(LayerDesc)), ("p_mu_out", ctypes.POINTER(LayerDesc)),
+                ("n_q_x_in", ctypes.c_int32), ("n_q_y_in", ctypes.c_int32), ("n_q_out", ctypes.c_int32),
+                ("q_x_in", ctypes.POINTER(LayerDesc)), ("q_y_in", ctypes.POINTER(LayerDesc)),
+                ("q_out", ctypes.POINTER(LayerDesc)), ("likelihood_scaling", ctypes.c_float)]
 
 
 class TransformParams(ctypes.Structure):
@@ -107,6 +110,7 @@ def load():
     lib.bp_tuning_get.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
     lib.bp_tuning_mode.argtypes = [i32, i32]
     lib.bp_rng_normal_host.argtypes = [i32, u64, u64, vp, ctypes.c_size_t]
+    lib.bp_cvae_elbo_host.argtypes = [vp, vp, vp, vp, i32, u64, tpp, i32, i32, vp, vp, vp]
     _lib = lib
     # the shipped formulation table: every process builds the same kernels for the same layer, so painted tiles
     # are bit-identical across processes (BARYON_PAINTER_TUNING_TABLE points at another table; "" = none)
@@ -161,16 +165,20 @@ class Net:
         self.precision, self.max_batch, self.device = precision, max_batch, device
 
     @classmethod
-    def create_cvae(cls, stacks, tile_hw, latent_hw, min_z_var, precision, max_batch, device):
+    def create_cvae(cls, stacks, tile_hw, latent_hw, min_z_var, precision, max_batch, device, likelihood_scaling=1.0):
         lib = load()
         keep, arrs = [], {}
-        for name in ("prior_network", "p_z_in", "p_y_z_in", "p_mu_out"):
+        for name in ("prior_network", "p_z_in", "p_y_z_in", "p_mu_out", "q_x_in", "q_y_in", "q_out"):
             arrs[name], k = make_layer_descs(stacks.get(name, []))
             keep += k
+        have_q = all(stacks.get(k) for k in ("q_x_in", "q_y_in", "q_out"))
         d = CvaeDesc(tile_hw[0], tile_hw[1], latent_hw[0], latent_hw[1], float(min_z_var),
                      len(stacks.get("prior_network", [])), len(stacks["p_z_in"]), len(stacks["p_y_z_in"]),
                      len(stacks["p_mu_out"]), arrs["prior_network"], arrs["p_z_in"], arrs["p_y_z_in"],
-                     arrs["p_mu_out"])
+                     arrs["p_mu_out"],
+                     len(stacks["q_x_in"]) if have_q else 0, len(stacks["q_y_in"]) if have_q else 0,
+                     len(stacks["q_out"]) if have_q else 0, arrs["q_x_in"], arrs["q_y_in"], arrs["q_out"],
+                     float(likelihood_scaling))
         h = ctypes.c_void_p()
         check(lib.bp_cvae_create(ctypes.byref(d), PRECISIONS[precision], int(max_batch), int(device),
                                  ctypes.byref(h)))
@@ -250,6 +258,21 @@ class Net:
                                                  ctypes.c_uint64(seed & (2 ** 64 - 1)), mean.ctypes.data,
                                                  var.ctypes.data, n))
         return mean, var
+
+    def cvae_elbo_host(self, x_tiles, y_tiles, eps, mode, seed, tparams, flags):
+        """(ELBO, KL_term, log_likelihood), z_mu, z_log_var of a batch (reference CVAE.forward, cvae.py:122-147)."""
+        n = x_tiles.shape[0]
+        x_tiles = np.ascontiguousarray(x_tiles, np.float32)
+        y_tiles = np.ascontiguousarray(y_tiles, np.float32)
+        eps = None if eps is None else np.ascontiguousarray(eps, np.float32)
+        stats = np.zeros(3, np.float64)
+        mu = np.empty((n, *self.latent_hw), np.float32)
+        lv = np.empty((n, *self.latent_hw), np.float32)
+        tp, keep = self._tp(*tparams)
+        check(load().bp_cvae_elbo_host(self.handle, x_tiles.ctypes.data, y_tiles.ctypes.data,
+                                       None if eps is None else eps.ctypes.data, mode, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                       ctypes.byref(tp), flags, n, stats.ctypes.data, mu.ctypes.data, lv.ctypes.data))
+        return stats, mu, lv
 
     def cgan_paint_host(self, tiles, tparams, flags, out=None):
         n = tiles.shape[0]

@@ -5,6 +5,7 @@
 //   CVAE.__init__ / load_state_dict       baryon_painter/models/cvae.py:9-61, painter.py:431-432
 //   CVAE.prior / sample_prior / P / sample_P   baryon_painter/models/cvae.py:82-120, 149-162
 //   CVAEPainter.paint (device part)       baryon_painter/painter.py:375-390
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -147,10 +148,11 @@ struct Stack {
 };
 
 enum { NET_CVAE = 0, NET_CGAN = 1 };
-enum { ST_PRIOR = 0, ST_PZ = 1, ST_PYZ = 2, ST_MU = 3, ST_GEN = 0 };
+enum { ST_PRIOR = 0, ST_PZ = 1, ST_PYZ = 2, ST_MU = 3, ST_QX = 4, ST_QY = 5, ST_QOUT = 6, ST_GEN = 0 };
+constexpr int kMaxStacks = 7;
 
 // ---- execution plan of the 16-bit window-GEMM engine (bp_wconv.cu) ------------------------------
-enum { V2_WCONV = 0, V2_F32CONV = 1, V2_TO_NHWC16 = 2, V2_TO_F32 = 3, V2_TAIL = 4 };
+enum { V2_WCONV = 0, V2_F32CONV = 1, V2_TO_NHWC16 = 2, V2_TO_F32 = 3, V2_TAIL = 4, V2_COPY_F32 = 5 };
 struct V2Op {
   int kind = V2_WCONV;
   int stack = -1, index = -1;     // layer this op executes (-1: layout conversion)
@@ -173,6 +175,10 @@ struct V2Plan {
   bool prior_conv0 = false;       // prior_network.0 runs inside the front kernel
   bool prior_from_cat = false;    // split precision: the prior network reads [y, z] of in_cat through a layout conversion
   FrontConvParams fc;
+  // recognition network Q (ELBO evaluation): q_x_in and q_y_in write the two channel halves of q_cat, q_out reads it
+  bool q_on = false;
+  std::vector<V2Op> qx_ops, qy_ops, qout_ops;
+  int q_cat = -1, q_out = -1;
 };
 
 struct bp_net {
@@ -180,7 +186,7 @@ struct bp_net {
   bool split = false;           // fp32-accurate tensor-core path: split-precision fp16 operands (BP_PREC_F32)
   int H = 0, W = 0, lh = 0, lw = 0, in_c = 0;
   float min_z_var = 1e-7f;
-  Stack st[4];
+  Stack st[kMaxStacks];
   int nstacks = 0;
   float* in_cat = nullptr;
   float* pool[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -193,13 +199,16 @@ struct bp_net {
   float *h_in = nullptr, *h_out = nullptr, *h_lat = nullptr;
   double *var_mean = nullptr, *var_m2 = nullptr;                      // variance maps: running moments (float64)
   float* var_rep = nullptr;                                           // ... and replicated tiles
+  float *xq = nullptr, *d_x = nullptr, *h_x = nullptr, *q_cat32 = nullptr, *q_out32 = nullptr;   // ELBO: transformed x, staging, fp32 Q tensors
+  double* d_sums = nullptr;                                           // ELBO: {sum of KL terms, sum of squared residuals}
+  float likelihood_scaling = 1.f;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr, out_stream = nullptr;
   std::vector<cudaEvent_t> ev_ready, ev_chunk_done, ev_out;   // per chunk of the pipelined host path
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int prior_valid = 0;
   bool debug = false;
-  std::vector<float*> dbg[4];
+  std::vector<float*> dbg[kMaxStacks];
   int dbg_n = 0;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per recorded layer launch
@@ -239,7 +248,7 @@ static int build_stack(const bp_layer_desc* descs, int n, int in_c, int H, int W
 static void destroy_net(bp_net* net) {
   if (!net) return;
   cudaSetDevice(net->device);
-  for (int s = 0; s < 4; ++s) {
+  for (int s = 0; s < kMaxStacks; ++s) {
     for (auto& l : net->st[s].layers) free_layer(&l);
     for (float* p : net->dbg[s]) cudaFree(p);
   }
@@ -251,6 +260,10 @@ static void destroy_net(bp_net* net) {
   cudaFree(net->latent); cudaFree(net->prior_all); cudaFree(net->prior_keep); cudaFree(net->params);
   cudaFree(net->d_in); cudaFree(net->d_out); cudaFree(net->d_lat);
   cudaFree(net->var_mean); cudaFree(net->var_m2); cudaFree(net->var_rep);
+  cudaFree(net->xq); cudaFree(net->d_x); cudaFree(net->q_cat32); cudaFree(net->q_out32); cudaFree(net->d_sums);
+  if (net->h_x) cudaFreeHost(net->h_x);
+  for (auto* v : {&net->v2.qx_ops, &net->v2.qy_ops, &net->v2.qout_ops})
+    for (auto& op : *v) wconv_free(op.w);
   if (net->h_in) cudaFreeHost(net->h_in);
   if (net->h_out) cudaFreeHost(net->h_out);
   if (net->h_lat) cudaFreeHost(net->h_lat);
@@ -292,6 +305,7 @@ static int finish_create(bp_net* net) {
   // path's decoder input) on the tensor-core paths
   for (int s = 0; s < net->nstacks; ++s) {
     if (net->prec == BP_PREC_F32_FFMA || (net->kind == NET_CVAE && s == ST_PZ)) mx = std::max(mx, net->st[s].max_floats);
+    if (net->kind == NET_CVAE && s >= ST_QX) continue;           // (the recognition network is not part of a paint)
     for (auto& l : net->st[s].layers) net->flops_per_tile += l.flops;
   }
   mx = std::max<size_t>(mx, 16);
@@ -322,6 +336,14 @@ static int finish_create(bp_net* net) {
   for (int i = 0; i < 2; ++i) {
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_in[i], cudaEventDisableTiming));
     BP_CUDA_TRY(cudaEventCreateWithFlags(&net->ev_done[i], cudaEventDisableTiming));
+  }
+  if (net->kind == NET_CVAE && !net->st[ST_QOUT].layers.empty()) {
+    const Stack& qx = net->st[ST_QX];
+    const Stack& qy = net->st[ST_QY];
+    BP_CUDA_TRY(cudaMalloc(&net->xq, sizeof(float) * HW * net->chunk));
+    BP_CUDA_TRY(cudaMalloc(&net->q_cat32, sizeof(float) * (size_t)(qx.out_c + qy.out_c) * qx.OH * qx.OW * net->chunk));
+    BP_CUDA_TRY(cudaMalloc(&net->q_out32, sizeof(float) * 2 * lhw * net->chunk));
+    BP_CUDA_TRY(cudaMalloc(&net->d_sums, sizeof(double) * 2));
   }
   if (net->prec != BP_PREC_F32_FFMA) {
     // the tensor-core paths (16-bit, and split-precision fp32) are the window-GEMM engine (bp_wconv.cu) or nothing: a network it cannot lower fails here
@@ -411,7 +433,7 @@ static int v2_time_layer(const WLayer* w, const ActDesc& out, const void* skip, 
 // lowers one layer sequence starting from act `cur`; the last layer of a `caller_out` sequence writes the
 // caller's fp32 tiles (tail stencil or fp32 kernel, inverse transform fused)
 static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vector<V2Op>& ops, bool caller_out,
-                        int* last_act) {
+                        int* last_act, int final_f32_act = -1) {
   V2Plan& P = net->v2;
   const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
   // the caller's fp32 tiles come from the tail stencil (1 -> 1 convolution) or, for a wider last layer, from its
@@ -589,14 +611,22 @@ static int v2_build_seq(bp_net* net, std::vector<V2Ref>& seq, int cur, std::vect
     }
   }
   if (!caller_out && !P.acts[cur].f32) {
-    // the sequence's consumer (latent sampling) reads fp32 NCHW
+    // the sequence's consumer (latent sampling; the concatenation in front of q_out) reads fp32 NCHW
     const ActDesc& c = P.acts[cur];
-    ActDesc a; a.C = c.C; a.Cp = c.C; a.H = c.H; a.W = c.W; a.f32 = true;
     V2Op cv; cv.kind = V2_TO_F32; cv.in = cur;
-    int rc = v2_new_act(net, a, &cv.out);
-    if (rc != BP_OK) return rc;
+    if (final_f32_act >= 0) {
+      cv.out = final_f32_act;              // a caller-owned view (channel slice of a wider fp32 tensor)
+    } else {
+      ActDesc a; a.C = c.C; a.Cp = c.C; a.H = c.H; a.W = c.W; a.f32 = true;
+      int rc = v2_new_act(net, a, &cv.out);
+      if (rc != BP_OK) return rc;
+    }
     ops.push_back(cv);
     cur = cv.out;
+  } else if (!caller_out && final_f32_act >= 0) {
+    V2Op cp; cp.kind = V2_COPY_F32; cp.in = cur; cp.out = final_f32_act;
+    ops.push_back(cp);
+    cur = cp.out;
   }
   if (last_act) *last_act = cur;
   return BP_OK;
@@ -727,6 +757,40 @@ static int v2_build(bp_net* net) {
       P.prior_on = true;
     }
   }
+  // ---- recognition network (ELBO evaluation only): inputs are fp32 planes (x' in net->xq, [y', z] in in_cat),
+  // brought into the engine's layout by conversions; outputs meet in the fp32 tensor q_cat32
+  if (!net->st[ST_QOUT].layers.empty()) {
+    const Stack& qx = net->st[ST_QX];
+    const Stack& qy = net->st[ST_QY];
+    const size_t hw = (size_t)net->H * net->W, qhw = (size_t)qx.OH * qx.OW;
+    const int cc = qx.out_c + qy.out_c;
+    auto view = [&](float* ptr, int C, int H, int W, long long bs) {
+      ActDesc v; v.ptr = ptr; v.C = C; v.Cp = C; v.H = H; v.W = W; v.f32 = true; v.f32_bs = bs;
+      P.acts.push_back(v);
+      return (int)P.acts.size() - 1;
+    };
+    const int x_in = view(net->xq, 1, net->H, net->W, (long long)hw);
+    const int y_in = view(net->in_cat + hw, 2, net->H, net->W, 3ll * hw);
+    const int cat_x = view(net->q_cat32, qx.out_c, qx.OH, qx.OW, (long long)cc * qhw);
+    const int cat_y = view(net->q_cat32 + (size_t)qx.out_c * qhw, qy.out_c, qy.OH, qy.OW, (long long)cc * qhw);
+    P.q_cat = view(net->q_cat32, cc, qx.OH, qx.OW, (long long)cc * qhw);
+    struct QSeq { int stack, in, fin; std::vector<V2Op>* ops; };
+    const QSeq seqs[3] = {{ST_QX, x_in, cat_x, &P.qx_ops}, {ST_QY, y_in, cat_y, &P.qy_ops}, {ST_QOUT, P.q_cat, -1, &P.qout_ops}};
+    for (const QSeq& q : seqs) {
+      std::vector<V2Ref> qs;
+      for (size_t i = 0; i < net->st[q.stack].layers.size(); ++i) {
+        V2Ref r{q.stack, (int)i, &net->st[q.stack].layers[i], false, 1};
+        r.w = v2_eligible(*r.l, &r.need_b, net->split);
+        qs.push_back(r);
+      }
+      int last = -1;
+      rc = v2_build_seq(net, qs, q.in, *q.ops, false, &last, q.fin);
+      if (rc != BP_OK) return rc;
+      if (q.stack == ST_QOUT) P.q_out = last;
+    }
+    BP_REQUIRE(P.acts[P.q_out].f32, BP_E_INVALID, "internal: q_out head is not fp32");
+    P.q_on = true;
+  }
   P.built = true;
   return BP_OK;
 }
@@ -842,6 +906,13 @@ static int v2_run(bp_net* net, std::vector<V2Op>& ops, float* final_out, long lo
       case V2_WCONV:
         rc = wconv_launch(op.w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, nb, s);
         break;
+      case V2_COPY_F32: {
+        const ActDesc& o = P.acts[op.out];
+        const size_t row = (size_t)in.C * in.H * in.W * sizeof(float);
+        BP_CUDA_TRY(cudaMemcpy2DAsync(o.ptr, o.elems_per_sample() * sizeof(float), in.ptr, in.elems_per_sample() * sizeof(float),
+                                      row, nb, cudaMemcpyDeviceToDevice, s));
+        break;
+      }
       case V2_TAIL: {
         TailParams t = P.tail;
         if (post.post != POST_NONE) { t.post = 1; t.post_k = post.k; t.post_shift = post.shift; }
@@ -1348,6 +1419,28 @@ int bp_cvae_create(const bp_cvae_desc* d, int precision, int max_batch, int devi
                 net->H, net->W);
       rc = BP_E_INVALID; break;
     }
+    if (d->n_q_out > 0) {
+      BP_REQUIRE(d->n_q_x_in > 0 && d->n_q_y_in > 0, BP_E_INVALID, "q_out without q_x_in / q_y_in");
+      rc = build_stack(d->q_x_in, d->n_q_x_in, 1, net->H, net->W, &net->st[ST_QX], "q_x_in");
+      if (rc != BP_OK) break;
+      rc = build_stack(d->q_y_in, d->n_q_y_in, 2, net->H, net->W, &net->st[ST_QY], "q_y_in");
+      if (rc != BP_OK) break;
+      const Stack& qx = net->st[ST_QX];
+      const Stack& qy = net->st[ST_QY];
+      if (!(qx.OH == qy.OH && qx.OW == qy.OW)) {
+        set_error("q_x_in and q_y_in outputs differ in size: (%d, %d) vs (%d, %d)", qx.OH, qx.OW, qy.OH, qy.OW);
+        rc = BP_E_INVALID; break;
+      }
+      rc = build_stack(d->q_out, d->n_q_out, qx.out_c + qy.out_c, qx.OH, qx.OW, &net->st[ST_QOUT], "q_out");
+      if (rc != BP_OK) break;
+      const Stack& qo = net->st[ST_QOUT];
+      if (!(qo.out_c == 2 && qo.OH == net->lh && qo.OW == net->lw)) {
+        set_error("Dimension of z_mu does not match dim_z: (%d, %d, %d) vs (1, %d, %d).", qo.out_c / 2, qo.OH, qo.OW, net->lh, net->lw);
+        rc = BP_E_INVALID; break;
+      }
+      net->nstacks = kMaxStacks;
+      net->likelihood_scaling = d->likelihood_scaling != 0.f ? d->likelihood_scaling : 1.f;
+    }
     rc = finish_create(net);
   } while (0);
   if (rc != BP_OK) { destroy_net(net); return rc; }
@@ -1536,6 +1629,108 @@ int bp_cvae_paint_variance_host(bp_net* net, const float* tiles, const bp_transf
   BP_CUDA_TRY(cudaStreamSynchronize(s));
   memcpy(mean_out, net->h_out, sizeof(float) * HW * n);
   memcpy(var_out, net->h_in, sizeof(float) * HW * n);
+  return BP_OK;
+}
+
+// Evidence lower bound of a batch (reference cvae.py:122-147 with Q :68-80); see the header for the formulas.
+int bp_cvae_elbo_host(bp_net* net, const float* x_tiles, const float* y_tiles, const float* eps, int latent_mode,
+                      uint64_t seed, const bp_transform_params* tp, int flags, int n, double* stats, float* z_mu,
+                      float* z_log_var) {
+  BP_REQUIRE(net && net->kind == NET_CVAE, BP_E_INVALID, "not a CVAE network");
+  BP_REQUIRE(!net->st[ST_QOUT].layers.empty(), BP_E_UNSUPPORTED, "the network was created without its recognition network (q_x_in / q_y_in / q_out)");
+  BP_REQUIRE(!net->st[ST_PRIOR].layers.empty(), BP_E_UNSUPPORTED, "network has no prior network");
+  BP_REQUIRE(n > 0 && n <= net->max_batch && x_tiles && y_tiles && stats && tp, BP_E_INVALID, "bad batch / null pointer");
+  BP_REQUIRE(latent_mode == BP_LATENT_EPS || latent_mode == BP_LATENT_SEED, BP_E_INVALID, "ELBO needs eps or a seed");
+  BP_REQUIRE(latent_mode == BP_LATENT_SEED || eps, BP_E_INVALID, "eps array missing");
+  BP_REQUIRE(!(flags & BP_FLAG_TRANSFORM) || (tp->sigma_in && tp->sigma_out), BP_E_INVALID, "sigma_in / sigma_out missing");
+  BP_CUDA_TRY(cudaSetDevice(net->device));
+  const size_t HW = (size_t)net->H * net->W, lhw = (size_t)net->lh * net->lw;
+  const int mb = net->max_batch;
+  cudaStream_t s = net->stream;
+  if (!net->d_x) {
+    BP_CUDA_TRY(cudaMalloc(&net->d_x, sizeof(float) * HW * net->max_batch));
+    BP_CUDA_TRY(cudaMallocHost(&net->h_x, sizeof(float) * HW * net->max_batch));
+  }
+  memcpy(net->h_in, y_tiles, sizeof(float) * HW * n);
+  memcpy(net->h_x, x_tiles, sizeof(float) * HW * n);
+  BP_CUDA_TRY(cudaMemcpyAsync(net->d_in, net->h_in, sizeof(float) * HW * n, cudaMemcpyHostToDevice, s));
+  BP_CUDA_TRY(cudaMemcpyAsync(net->d_x, net->h_x, sizeof(float) * HW * n, cudaMemcpyHostToDevice, s));
+  if (latent_mode == BP_LATENT_EPS) {
+    memcpy(net->h_lat, eps, sizeof(float) * lhw * n);
+    BP_CUDA_TRY(cudaMemcpyAsync(net->d_lat, net->h_lat, sizeof(float) * lhw * n, cudaMemcpyHostToDevice, s));
+  }
+  // sigma_in -> params[0..], sigma_out -> params[mb..] (here: the FORWARD transform of x), aux -> params[2 mb..]
+  int rc = upload_params(net, tp, (flags & BP_FLAG_TRANSFORM) ? (BP_FLAG_TRANSFORM | BP_FLAG_INVERSE) : 0, n, s);
+  if (rc != BP_OK) return rc;
+  BP_CUDA_TRY(cudaMemsetAsync(net->d_sums, 0, sizeof(double) * 2, s));
+  const int do_t = (flags & BP_FLAG_TRANSFORM) ? 1 : 0;
+  const Stack& qx = net->st[ST_QX];
+  const Stack& qy = net->st[ST_QY];
+  const size_t qhw = (size_t)qx.OH * qx.OW;
+  const int cc = qx.out_c + qy.out_c;
+  V2Plan& P = net->v2;
+  PostOp none;
+  for (int c0 = 0; c0 < n; c0 += net->chunk) {
+    const int nb = std::min(net->chunk, n - c0);
+    // x' and [y', z] as fp32 planes
+    rc = launch_prepare(net->d_x + (size_t)c0 * HW, net->xq, (long long)HW, 0, -1, net->params + mb + c0, net->params + 2 * mb + c0,
+                        tp->k_out, tp->shift_out, do_t, nb, (int)HW, s);
+    if (rc != BP_OK) return rc;
+    rc = launch_prepare(net->d_in + (size_t)c0 * HW, net->in_cat, 3 * (long long)HW, 1, 2, net->params + c0,
+                        net->params + 2 * mb + c0, tp->k_in, tp->shift_in, do_t, nb, (int)HW, s);
+    if (rc != BP_OK) return rc;
+    // recognition network -> (z_mu, z_log_var), into buffers of its own (the prior network below and the decoder
+    // reuse the rotating pool)
+    const float* q_out = nullptr;
+    if (P.built && P.q_on) {
+      rc = v2_run(net, P.qx_ops, nullptr, 0, none, nb, s);
+      if (rc == BP_OK) rc = v2_run(net, P.qy_ops, nullptr, 0, none, nb, s);
+      if (rc == BP_OK) rc = v2_run(net, P.qout_ops, nullptr, 0, none, nb, s);
+      if (rc != BP_OK) return rc;
+      q_out = static_cast<const float*>(P.acts[P.q_out].ptr);
+    } else {
+      ActRef in;
+      in.ptr = net->xq; in.bs = (long long)HW;
+      rc = run_stack(net, ST_QX, in, net->q_cat32, (long long)cc * qhw, none, nb, s, nullptr);
+      if (rc != BP_OK) return rc;
+      in.ptr = net->in_cat + HW; in.bs = 3 * (long long)HW;
+      rc = run_stack(net, ST_QY, in, net->q_cat32 + (size_t)qx.out_c * qhw, (long long)cc * qhw, none, nb, s, nullptr);
+      if (rc != BP_OK) return rc;
+      in.ptr = net->q_cat32; in.bs = (long long)cc * qhw;
+      rc = run_stack(net, ST_QOUT, in, net->q_out32, 2 * (long long)lhw, none, nb, s, nullptr);
+      if (rc != BP_OK) return rc;
+      q_out = net->q_out32;
+    }
+    // prior network
+    float* prior_out = nullptr;
+    rc = cvae_chunk_front(net, net->d_in, tp, flags, c0, nb, true, s, &prior_out);
+    if (rc != BP_OK) return rc;
+    // z = z_mu + eps * (exp(z_log_var / 2) + min_z_var); Q's (z_mu, z_log_var) are kept in prior_all for the caller
+    rc = launch_sample_z(q_out, latent_mode == BP_LATENT_EPS ? net->d_lat + (size_t)c0 * lhw : nullptr, net->latent,
+                         net->prior_all + (size_t)c0 * lhw, net->prior_all + ((size_t)mb + c0) * lhw, net->min_z_var, nb,
+                         (int)lhw, latent_mode, seed, (uint64_t)c0 * lhw, s);
+    if (rc != BP_OK) return rc;
+    rc = launch_kl_sum(q_out, prior_out, nb, (int)lhw, net->d_sums, s);
+    if (rc != BP_OK) return rc;
+    // x_mu = P(z, y) (no inverse transform), then the squared residual against x'
+    rc = cvae_chunk_back(net, net->d_in, net->latent, tp, flags & ~BP_FLAG_INVERSE, c0, nb, net->d_out, s);
+    if (rc != BP_OK) return rc;
+    rc = launch_sqdiff_sum(net->xq, net->d_out, HW * nb, net->d_sums + 1, s);
+    if (rc != BP_OK) return rc;
+  }
+  double sums[2] = {0, 0};
+  BP_CUDA_TRY(cudaMemcpyAsync(sums, net->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s));
+  BP_CUDA_TRY(cudaStreamSynchronize(s));
+  const double kl = 0.5 / n * sums[0];
+  const double ll = -0.5 * log(2.0 * 3.14159265358979323846) + (-0.5 * sums[1]) / n;
+  stats[0] = -kl + (double)net->likelihood_scaling * ll;
+  stats[1] = kl;
+  stats[2] = ll;
+  net->prior_valid = n;
+  if (z_mu && z_log_var) {
+    BP_CUDA_TRY(cudaMemcpy(z_mu, net->prior_all, sizeof(float) * lhw * n, cudaMemcpyDeviceToHost));
+    BP_CUDA_TRY(cudaMemcpy(z_log_var, net->prior_all + (size_t)mb * lhw, sizeof(float) * lhw * n, cudaMemcpyDeviceToHost));
+  }
   return BP_OK;
 }
 

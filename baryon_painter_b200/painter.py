@@ -111,9 +111,11 @@ class CVAEModel:
         if self._net is not None:
             self._net.close()
         folded = {name: _arch.fold_stack(self.stacks[name], self._state)
-                  for name in ("prior_network", "p_z_in", "p_y_z_in", "p_mu_out") if name in self.stacks}
+                  for name in ("prior_network", "p_z_in", "p_y_z_in", "p_mu_out", "q_x_in", "q_y_in", "q_out")
+                  if name in self.stacks}
         self._net = _lib.Net.create_cvae(folded, self.dim_y[1:], self.dim_z[1:], self.min_z_var, self.precision,
-                                         self.max_batch, _device_index(self.device))
+                                         self.max_batch, _device_index(self.device),
+                                         self.architecture.get("likelihood_scaling", 1.0))
 
     @property
     def net(self):
@@ -145,6 +147,34 @@ class CVAEModel:
         out = self.net.cvae_paint_host(y.reshape(n, *self.dim_y[1:]), lat, mode, seed,
                                        (None, None, aux, 1.0, 0.0, 1.0, 0.0), 0)
         return torch.from_numpy(out.reshape(n, 1, *self.dim_y[1:]))
+
+    def forward(self, x, y, aux_label=None, eps=None, seed=0):
+        """Evidence lower bound of a batch of already-transformed (x, y) pairs (reference cvae.py:122-147, with the
+        recognition network Q :68-80), evaluated on the device.  ``eps`` (N,1,h,w) replaces the ``torch.randn`` draw of
+        ``sample_z``.  Sets ``ELBO``, ``KL_term``, ``log_likelihood``, ``z_mu``, ``z_log_var`` like the reference."""
+        import torch
+        x = np.asarray(x.detach().cpu() if hasattr(x, "detach") else x, np.float32)
+        y = np.asarray(y.detach().cpu() if hasattr(y, "detach") else y, np.float32)
+        n = y.shape[0]
+        aux = np.broadcast_to(np.asarray(aux_label.detach().cpu() if hasattr(aux_label, "detach") else aux_label,
+                                         np.float32).reshape(-1), (n,))
+        self.ensure_batch(n)
+        mode = _lib.BP_LATENT_SEED if eps is None else _lib.BP_LATENT_EPS
+        stats, mu, lv = self.net.cvae_elbo_host(x.reshape(n, *self.dim_x[1:]), y.reshape(n, *self.dim_y[1:]),
+                                                None if eps is None else np.asarray(eps, np.float32).reshape(n, *self.dim_z[1:]),
+                                                mode, seed, (None, None, aux, 1.0, 0.0, 1.0, 0.0), 0)
+        self.ELBO, self.KL_term = torch.tensor(stats[0]), torch.tensor(stats[1])
+        self.log_likelihood = torch.tensor([stats[2]])
+        self.z_mu, self.z_log_var = torch.from_numpy(mu[:, None]), torch.from_numpy(lv[:, None])
+        return self.ELBO
+
+    __call__ = forward
+
+    def get_stats(self):
+        return (self.ELBO.item(), -self.KL_term.item(), *self.log_likelihood.numpy())
+
+    def get_stats_labels(self):
+        return ["ELBO", "KL_term"] + ["log_likelihood_{}".format(i) for i in range(self.n_x_features)]
 
     def prior(self, y, aux_label=None):
         import torch
@@ -323,6 +353,25 @@ class CVAEPainter(Painter):
         if inverse_transform and self.inverse_transform is not None:
             return out[0]
         return out.reshape(1, 1, *out.shape[-2:])
+
+    def elbo(self, x_tiles, y_tiles, z=0.0, eps=None, seed=0):
+        """Evidence lower bound of raw (pressure, dark matter) tile pairs at redshift(s) ``z``: the dataset transforms
+        of both fields fused on the device, then ``CVAE.forward`` (what the reference's ``validate`` evaluates per
+        batch, painter.py:295-367).  Returns ``(ELBO, KL_term, log_likelihood)``."""
+        x_tiles, y_tiles = np.asarray(x_tiles, np.float32), np.asarray(y_tiles, np.float32)
+        n = y_tiles.shape[0]
+        zs = np.broadcast_to(np.asarray(z, np.float64).reshape(-1), (n,))
+        # forward transforms of BOTH fields: sigma_in for the input field, sigma_out for the label field
+        p_in = [self.transform.gpu_params(self.input_field, float(v)) for v in zs]
+        p_x = [self.transform.gpu_params(self.label_fields[0], float(v)) for v in zs]
+        s_in = np.array([q[1] for q in p_in], np.float32)
+        s_x = np.array([q[1] for q in p_x], np.float32)
+        self.model.ensure_batch(n)
+        mode = _lib.BP_LATENT_SEED if eps is None else _lib.BP_LATENT_EPS
+        stats, mu, lv = self.model.net.cvae_elbo_host(
+            x_tiles, y_tiles, None if eps is None else np.asarray(eps, np.float32).reshape(n, *self.model.dim_z[1:]), mode, seed,
+            (s_in, s_x, zs.astype(np.float32), p_in[0][2], p_in[0][3], p_x[0][2], p_x[0][3]), _lib.BP_FLAG_TRANSFORM)
+        return float(stats[0]), float(stats[1]), float(stats[2])
 
     def paint_variance(self, tiles, z=0.0, n_draws=64, seed=0):
         """Per-pixel mean and variance of the painted pressure over ``n_draws`` latent draws per

@@ -179,6 +179,33 @@ class CVAEOracle:
                 taps.append(("latent", z))
             return self.P(z, y, aux, taps)
 
+    def Q(self, x, y, aux):
+        """recognition network (reference cvae.py:68-80) -> (z_mu, z_log_var)"""
+        h_x = run_sequential(self.arch["q_x_in"], self.sd, "q_x_in", x)
+        h_y = run_sequential(self.arch["q_y_in"], self.sd, "q_y_in", merge_aux_label(y, aux))
+        h = run_sequential(self.arch["q_x_y_out"], self.sd, "q_out", torch.cat([h_x, h_y], dim=1))
+        return h[:, 0], h[:, 1]
+
+    def forward(self, x, y, aux, eps):
+        """evidence lower bound of a batch of transformed (x, y) pairs (reference cvae.py:122-147; fixed variance,
+        L = 1, beta_KL = 1, ``torch.randn`` replaced by ``eps``) -> dict(ELBO, KL_term, log_likelihood, z_mu, z_log_var)"""
+        import math
+        with torch.no_grad():
+            x = torch.as_tensor(x, dtype=self.dtype)
+            y = torch.as_tensor(y, dtype=self.dtype)
+            aux = torch.as_tensor(aux, dtype=self.dtype)
+            z_mu, z_log_var = self.Q(x, y, aux)
+            z = self.sample_z(z_mu, z_log_var, torch.as_tensor(eps, dtype=self.dtype).view(1, *z_mu.size()))
+            M = x.size(0)
+            pm, plv = self.prior(y, aux)
+            pv = torch.exp(plv)
+            KL = 0.5 / M * torch.sum((pm - z_mu) ** 2 / pv + torch.exp(z_log_var) / pv + plv - z_log_var - 1)
+            x_mu = self.P(z, y, aux)
+            ll = -0.5 * math.log(2 * math.pi) + 1 / M * (-0.5 * (x - x_mu) ** 2).sum(dim=[3, 2, 0])
+            scaling = self.arch.get("likelihood_scaling", 1.0)
+            return dict(ELBO=float(-KL + scaling * ll.sum()), KL_term=float(KL), log_likelihood=ll.numpy().astype(np.float64),
+                        z_mu=z_mu.numpy(), z_log_var=z_log_var.numpy())
+
     def paint(self, tile, z, stats, latent=None, eps=None, transform=True, inverse_transform=True):
         """One tile, reference ``paint`` semantics -> float32 (H, W)."""
         y = forward_transform(tile, z, stats) if transform else tile

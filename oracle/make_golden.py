@@ -20,6 +20,8 @@ cvae_t128.npz         tile 128 network, 4 tiles x z in {0, 0.3, 1.0, 2.5}: paint
                       mode E (eps supplied) and mode L (latent supplied), (mu, log-var)
 cvae_t512.npz         fiducial 512 network, 2 tiles: painted tiles, mode E at z=0 and
                       mode L at z=0.7
+cvae_t64_elbo.npz     tile 64 network, 3 (pressure, dark matter) pairs: CVAE.forward's ELBO, KL term,
+                      log-likelihood and the recognition network's (z_mu, z_log_var)
 fiducial_meta.json    plain keys + stats table + architecture lifted from the shipped
                       trained_models/CVAE/fiducial/model_meta
 tiling.json           reference generate_tiling / make_weight_map / get_tile known answers
@@ -141,6 +143,40 @@ def make_cvae(tile_size, n_tiles, zs, seed, with_layers=False):
     return out
 
 
+def make_elbo(tile_size, n_tiles, zs, seed):
+    """reference ``CVAE.forward`` (cvae.py:122-147) with ``torch.randn`` pinned to ``eps``: ELBO, KL term,
+    log-likelihood and Q's (z_mu, z_log_var) of a batch of (pressure, dark-matter) tile pairs."""
+    A = arch.fiducial_cvae_architecture(tile_size)
+    sd = synthetic.synthetic_cvae_state_dict(A, seed=seed)
+    stats = transforms.fiducial_stats()
+    painter = ref_shims.reference_painter(A, sd, stats)
+    oracle = cvae_oracle.CVAEOracle(A, sd)
+    lat_hw = A["dim_z"][1:]
+    dm = synthetic.synthetic_dm_tiles(n_tiles, tile_size, seed0=100 * seed + 50)
+    # a pressure-like positive field correlated with the dark matter
+    pr = (0.05 * dm ** 1.5 * np.random.default_rng(seed).lognormal(0.0, 0.3, dm.shape)).astype(np.float32)
+    eps = synthetic.synthetic_latents(n_tiles, lat_hw, seed=3)
+    y = np.stack([painter.transform(dm[i], field="dm", z=float(zs[i])) for i in range(n_tiles)]).astype(np.float32)
+    x = np.stack([painter.transform(pr[i], field="pressure", z=float(zs[i])) for i in range(n_tiles)]).astype(np.float32)
+    m = painter.model
+    m.train(False)
+    real_randn = torch.randn
+    try:
+        torch.randn = lambda size, device=None: torch.tensor(eps).view(*size)      # sample_z's only draw
+        with torch.no_grad():
+            elbo = m.forward(torch.tensor(x), torch.tensor(y), torch.tensor(np.asarray(zs, np.float32)))
+    finally:
+        torch.randn = real_randn
+    o = oracle.forward(x, y, np.asarray(zs, np.float32), eps)
+    assert float(elbo) == o["ELBO"] and float(m.KL_term) == o["KL_term"], "oracle != reference"
+    assert np.array_equal(m.z_mu.numpy(), o["z_mu"]) and np.array_equal(m.z_log_var.numpy(), o["z_log_var"])
+    return {"seed": np.int64(seed), "tile_size": np.int64(tile_size), "z": np.asarray(zs, np.float64), "eps": eps,
+            "dm_seed0": np.int64(100 * seed + 50), "pressure": pr, "x": x, "y": y,
+            "ELBO": np.float64(float(elbo)), "KL_term": np.float64(float(m.KL_term)),
+            "log_likelihood": m.log_likelihood.numpy().astype(np.float64),
+            "z_mu": m.z_mu.numpy(), "z_log_var": m.z_log_var.numpy()}
+
+
 def make_meta_json():
     path = os.path.join(ref_shims.REFERENCE_ROOT, "trained_models", "CVAE", "fiducial", "model_meta")
     d = meta.read_model_meta(path)
@@ -193,6 +229,7 @@ def main():
     full["painted_E"] = full["painted_E"][:1]          # tile 0, mode E, z=0
     full["painted_L"] = full["painted_L"][1:]          # tile 1, mode L, z=0.7
     np.savez(os.path.join(GOLDEN, "cvae_t512.npz"), **full)
+    np.savez(os.path.join(GOLDEN, "cvae_t64_elbo.npz"), **make_elbo(64, 3, [0.0, 0.5, 1.2], seed=5))
     with open(os.path.join(GOLDEN, "fiducial_meta.json"), "w") as f:
         json.dump(make_meta_json(), f, indent=1, sort_keys=True)
     with open(os.path.join(GOLDEN, "tiling.json"), "w") as f:

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of the header structs have the C layout the header implies."""
     from baryon_painter_b200 import _lib
     assert ctypes.sizeof(_lib.LayerDesc) == 64 and _lib.LayerDesc.weight.offset == 40
-    assert ctypes.sizeof(_lib.CvaeDesc) == 72 and _lib.CvaeDesc.prior.offset == 40
+    assert ctypes.sizeof(_lib.CvaeDesc) == 120 and _lib.CvaeDesc.prior.offset == 40 and _lib.CvaeDesc.q_x_in.offset == 88
     assert ctypes.sizeof(_lib.TransformParams) == 40 and _lib.TransformParams.k_in.offset == 24
 
 

@@ -363,3 +363,23 @@ def test_variance_maps_single_draw():
     assert np.all(v == 0) and np.all(np.isfinite(m))
     m10, v10 = p.paint_variance(tiles, z=zs, n_draws=10, seed=5)          # chunk 16 // 3 tiles -> 5 draws per pass
     assert np.all(np.isfinite(m10)) and np.all(v10 >= 0) and v10.max() > 0
+
+
+@pytest.mark.parametrize("precision,tol,tol_z", [("fp32", 1e-4, 2e-5), ("fp32-ffma", 1e-4, 2e-5), ("fp16", 1e-2, 5e-3)])
+def test_elbo_vs_reference_golden(precision, tol, tol_z):
+    """the recognition network Q and the ELBO forward (reference cvae.py:68-80, 122-147) on the
+    device, against the reference's own CVAE.forward (golden): ELBO, KL term, log-likelihood, Q's (z_mu, z_log_var).
+    Both entry points: already-transformed pairs (CVAEModel.forward) and raw tiles (CVAEPainter.elbo)."""
+    g = np.load(os.path.join(GOLDEN, "cvae_t64_elbo.npz"))
+    p = _painter(64, int(g["seed"]), precision)
+    zs = g["z"]
+    elbo = p.model.forward(g["x"], g["y"], aux_label=zs.astype(np.float32), eps=g["eps"])
+    assert abs(float(elbo) - float(g["ELBO"])) <= tol * abs(float(g["ELBO"]))
+    assert abs(float(p.model.KL_term) - float(g["KL_term"])) <= 10 * tol * abs(float(g["KL_term"])) + 1e-6
+    assert abs(float(p.model.log_likelihood[0]) - float(g["log_likelihood"][0])) <= tol * abs(float(g["log_likelihood"][0]))
+    assert rel_l2(p.model.z_mu.numpy(), g["z_mu"]) <= tol_z and rel_l2(p.model.z_log_var.numpy(), g["z_log_var"]) <= 10 * tol_z
+    assert p.model.get_stats()[0] == float(elbo) and p.model.get_stats_labels()[:2] == ["ELBO", "KL_term"]
+    from baryon_painter_b200 import synthetic
+    dm = synthetic.synthetic_dm_tiles(3, 64, seed0=int(g["dm_seed0"]))
+    e2, kl2, ll2 = p.elbo(g["pressure"], dm, z=zs, eps=g["eps"])
+    assert abs(e2 - float(g["ELBO"])) <= 2 * tol * abs(float(g["ELBO"]))

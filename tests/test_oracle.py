@@ -123,3 +123,16 @@ def test_cgan_oracle_runs_small():
     tile = synthetic.synthetic_dm_tiles(1, 64, seed0=3)[0]
     out = orc.paint(tile, 0.5, transforms.fiducial_stats())
     assert out.shape == (64, 64) and out.dtype == np.float32 and np.all(np.isfinite(out))
+
+
+def test_oracle_forward_matches_reference_golden():
+    """Q + ELBO restatement (oracle.forward) against the reference's own CVAE.forward (golden written by
+    oracle/make_golden.py with torch.randn pinned): bit-identical on this torch build."""
+    import torch
+    torch.set_num_threads(4)
+    g = np.load(os.path.join(GOLDEN, "cvae_t64_elbo.npz"))
+    A = arch.fiducial_cvae_architecture(int(g["tile_size"]))
+    o = cvae_oracle.CVAEOracle(A, synthetic.synthetic_cvae_state_dict(A, seed=int(g["seed"])))
+    r = o.forward(g["x"], g["y"], g["z"].astype(np.float32), g["eps"])
+    assert r["ELBO"] == pytest.approx(float(g["ELBO"]), rel=1e-6) and r["KL_term"] == pytest.approx(float(g["KL_term"]), rel=1e-6)
+    assert np.allclose(r["z_mu"], g["z_mu"], rtol=1e-5, atol=1e-7) and np.allclose(r["log_likelihood"], g["log_likelihood"], rtol=1e-6)
