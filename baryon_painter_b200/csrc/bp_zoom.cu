@@ -92,6 +92,175 @@ __global__ void zoom_filter_kernel(double* __restrict__ work, int side, int ntil
 #undef C
 }
 
+// ---- the same recursions for LONG lines, parallel along the line -------------------------------------------
+// Both recursions forget their state geometrically: |z|^i drops below 1e-18 after `horizon` = ceil(ln 1e-18 / ln|z|)
+// samples (32 for the cubic pole, 50 / 14 for the quintic ones).  So (1) the boundary sums of scipy's initialisation
+// stop after `horizon` terms and z^(len-1) vanishes from them -- same float64 result to the last bits; (2) a line is
+// cut into segments of kSeg samples, each warmed up from a zero state over the `horizon` samples in front of it
+// (behind it for the anticausal sweep): every (line, segment) pair is an independent thread, which fills the
+// machine even for the four 7000^2 crops of a near lightcone plane.  Sweeps are out of place (in -> out), because a
+// segment's warm-up reads what its neighbour is about to overwrite.
+constexpr int kSeg = 256;
+__device__ __forceinline__ int zoom_horizon(double z) { return (int)ceil(-41.4465 / log(fabs(z))); }
+
+// value of sample i0 - 1 of the causal recursion (state entering segment [i0, ...)), reading `in` with stride st
+__device__ __forceinline__ double zoom_causal_enter(const double* in, size_t st, int i0, double z, double g, int H, int mirror,
+                                                    bool* wrote0, double* first) {
+  *wrote0 = false;
+  if (i0 == 0) {
+    double z_i = 1.0, s = 0.0;
+    for (int i = 0; i < H; ++i) {
+      s += z_i * (g * in[i * st]);
+      z_i *= z;
+    }
+    *first = mirror ? s : s * z + g * in[0];
+    *wrote0 = true;
+    return *first;
+  }
+  double prev = 0.0;
+  for (int i = i0 - H; i < i0; ++i) prev = g * in[i * st] + z * prev;
+  return prev;
+}
+
+// columns: thread = (column, segment); neighbouring threads read neighbouring addresses
+__global__ void zoom_cols_causal_kernel(const double* __restrict__ in, double* __restrict__ out, int side, int ntiles, int mirror,
+                                        double z, double g) {
+  const int nseg = (side + kSeg - 1) / kSeg;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)ntiles * nseg * side) return;
+  const int l = (int)(t % side), j = (int)((t / side) % nseg), n = (int)(t / ((long long)side * nseg));
+  const size_t st = (size_t)side, off = (size_t)n * side * side + l;
+  const int H = zoom_horizon(z), i0 = j * kSeg, i1 = min(side, i0 + kSeg);
+  bool wrote0;
+  double first;
+  double prev = zoom_causal_enter(in + off, st, i0, z, g, H, mirror, &wrote0, &first);
+  if (wrote0) out[off] = first;
+  for (int i = wrote0 ? 1 : i0; i < i1; ++i) {
+    prev = g * in[off + i * st] + z * prev;
+    out[off + i * st] = prev;
+  }
+}
+// in = causal output.  The last sample starts from scipy's exact end condition; other segments warm up from zero
+__global__ void zoom_cols_anticausal_kernel(const double* __restrict__ in, double* __restrict__ out, int side, int ntiles,
+                                            int mirror, double z) {
+  const int nseg = (side + kSeg - 1) / kSeg;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)ntiles * nseg * side) return;
+  const int l = (int)(t % side), j = (int)((t / side) % nseg), n = (int)(t / ((long long)side * nseg));
+  const size_t st = (size_t)side, off = (size_t)n * side * side + l;
+  const int H = zoom_horizon(z), i0 = j * kSeg, i1 = min(side, i0 + kSeg);
+  double next;
+  int i;
+  if (i1 + H >= side - 1) {            // close enough to the end: start from the exact end condition
+    const double a = in[off + (size_t)(side - 2) * st], b = in[off + (size_t)(side - 1) * st];
+    next = mirror ? (z * a + b) * z / (z * z - 1.0) : b * (z / (z - 1.0));
+    if (i1 == side) out[off + (size_t)(side - 1) * st] = next;
+    i = side - 2;
+  } else {
+    next = 0.0;
+    i = i1 + H - 1;
+  }
+  for (; i >= i1; --i) next = z * (next - in[off + i * st]);
+  for (; i >= i0; --i) {
+    next = z * (next - in[off + i * st]);
+    out[off + i * st] = next;
+  }
+}
+
+// rows: warp = (32 rows, segment); 32 x 32 chunks go through shared memory so that global accesses stay coalesced
+// (lane = column while loading / storing, lane = row while recursing)
+constexpr int kRowWarps = 4;
+template <bool CAUSAL>
+__global__ void __launch_bounds__(32 * kRowWarps) zoom_rows_kernel(const double* __restrict__ in, double* __restrict__ out, int side,
+                                                                  int ntiles, int mirror, double z, double g) {
+  __shared__ double sm[kRowWarps][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rblocks = (side + 31) / 32, nseg = (side + kSeg - 1) / kSeg;
+  const long long wid = (long long)blockIdx.x * kRowWarps + warp;
+  if (wid >= (long long)ntiles * rblocks * nseg) return;
+  const int j = (int)(wid % nseg), rb = (int)((wid / nseg) % rblocks), n = (int)(wid / ((long long)nseg * rblocks));
+  const int r0 = rb * 32, nrows = min(32, side - r0);
+  const size_t base = (size_t)n * side * side + (size_t)r0 * side;
+  double (*tile)[33] = sm[warp];
+  const int H = zoom_horizon(z), i0 = j * kSeg, i1 = min(side, i0 + kSeg);
+  auto load = [&](int c0) {           // columns c0 .. c0 + 31 of the 32 rows
+    __syncwarp();
+    for (int r = 0; r < nrows; ++r) tile[r][lane] = (c0 + lane >= 0 && c0 + lane < side) ? in[base + (size_t)r * side + c0 + lane] : 0.0;
+    __syncwarp();
+  };
+  auto store = [&](int c0, int lo, int hi) {   // columns [lo, hi) of the chunk at c0
+    __syncwarp();
+    for (int r = 0; r < nrows; ++r)
+      if (c0 + lane >= lo && c0 + lane < hi) out[base + (size_t)r * side + c0 + lane] = tile[r][lane];
+    __syncwarp();
+  };
+  if (CAUSAL) {
+    double prev = 0.0;
+    int c_begin;                      // first chunk whose samples are written
+    if (i0 == 0) {
+      double z_i = 1.0, s = 0.0;
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        load(c0);
+        for (int k = 0; k < 32 && c0 + k < H; ++k) {
+          s += z_i * (g * tile[lane][k]);
+          z_i *= z;
+        }
+      }
+      prev = s;                       // becomes sample 0 below (mirror: s; reflect: s z + g c[0])
+      c_begin = 0;
+    } else {
+      const int w0 = ((i0 - H) / 32) * 32;       // warm-up over [i0 - H, i0)
+      for (int c0 = w0; c0 < i0; c0 += 32) {
+        load(c0);
+        for (int k = 0; k < 32; ++k)
+          if (c0 + k >= i0 - H && c0 + k < i0) prev = g * tile[lane][k] + z * prev;
+      }
+      c_begin = i0;
+    }
+    for (int c0 = c_begin; c0 < i1; c0 += 32) {
+      load(c0);
+      for (int k = 0; k < 32 && c0 + k < i1; ++k) {
+        if (c0 + k == 0) prev = mirror ? prev : prev * z + g * tile[lane][0];
+        else prev = g * tile[lane][k] + z * prev;
+        tile[lane][k] = prev;
+      }
+      store(c0, i0, i1);
+    }
+  } else {
+    double next = 0.0;
+    int i;                            // next sample to process (descending)
+    if (i1 + H >= side - 1) {
+      // exact end condition from the causal output's last two samples
+      const int cl = ((side - 1) / 32) * 32;
+      load(cl);
+      const double b = tile[lane][side - 1 - cl];
+      double a;
+      if (side - 2 >= cl) a = tile[lane][side - 2 - cl];
+      else { load(cl - 32); a = tile[lane][31]; }
+      next = mirror ? (z * a + b) * z / (z * z - 1.0) : b * (z / (z - 1.0));
+      i = side - 2;
+      if (i1 == side) {               // this segment owns the last sample
+        load(cl);
+        tile[lane][side - 1 - cl] = next;
+        store(cl, side - 1, side);
+      }
+    } else {
+      i = i1 + H - 1;
+    }
+    const double end_val = next;      // (only meaningful on the exact-end branch)
+    for (int c0 = (i / 32) * 32; c0 + 31 >= i0 && i >= i0; c0 -= 32) {
+      load(c0);
+      if (i1 == side && c0 <= side - 1 && side - 1 < c0 + 32) tile[lane][side - 1 - c0] = end_val;   // keep the last sample
+      for (int k = min(31, i - c0); k >= 0 && c0 + k >= i0; --k) {
+        next = z * (next - tile[lane][k]);
+        tile[lane][k] = next;
+        i = c0 + k - 1;
+      }
+      store(c0, i0, i1);
+    }
+  }
+}
+
 __device__ __forceinline__ int zoom_fold(int idx, int len, int mirror) {
   if (idx >= 0 && idx < len) return idx;
   if (len <= 1) return 0;
@@ -224,16 +393,38 @@ namespace {
 constexpr double kPole5a = -0.43057534709997381;       // sqrt(67.5 - sqrt(4436.25)) + sqrt(26.25) - 6.5
 constexpr double kPole5b = -0.043096288203264652;      // sqrt(67.5 + sqrt(4436.25)) - sqrt(26.25) - 6.5
 
-// prefilter (rows, then columns) of n cropped tiles already in `work`
-int zoom_prefilter(double* work, int side, int n, int order, int mirror, cudaStream_t s) {
+// prefilter (rows, then columns) of n cropped tiles already in `work`; `tmp` is a second buffer of the same size
+int zoom_prefilter(double* work, double* tmp, int side, int n, int order, int mirror, cudaStream_t s) {
   const long long lines = (long long)n * side;
   const int fb = 64;
   const int npoles = order == 3 ? 1 : 2;
   const double p0 = order == 3 ? kPole : kPole5a, p1 = kPole5b;
   // scipy filters axis by axis; the recursions along different axes commute
-  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, (long long)side, 1LL, mirror, npoles, p0, p1);
-  zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, 1LL, (long long)side, mirror, npoles, p0, p1);
-  launch_counter() += 2;
+  if (side > 2 * kSeg) {     // long lines: segment-parallel out-of-place sweeps (every horizon is <= 50 < kSeg)
+    double gain = 1.0;
+    for (int p = 0; p < npoles; ++p) {
+      const double z = p == 0 ? p0 : p1;
+      gain *= (1.0 - z) * (1.0 - 1.0 / z);
+    }
+    const int nseg = (side + kSeg - 1) / kSeg;
+    const long long rwarps = (long long)n * ((side + 31) / 32) * nseg, cthreads = lines * nseg;
+    const unsigned rgrid = (unsigned)((rwarps + kRowWarps - 1) / kRowWarps), cgrid = (unsigned)((cthreads + 127) / 128);
+    for (int p = 0; p < npoles; ++p) {
+      const double z = p == 0 ? p0 : p1;
+      zoom_rows_kernel<true><<<rgrid, 32 * kRowWarps, 0, s>>>(work, tmp, side, n, mirror, z, p == 0 ? gain : 1.0);
+      zoom_rows_kernel<false><<<rgrid, 32 * kRowWarps, 0, s>>>(tmp, work, side, n, mirror, z, 1.0);
+    }
+    for (int p = 0; p < npoles; ++p) {
+      const double z = p == 0 ? p0 : p1;
+      zoom_cols_causal_kernel<<<cgrid, 128, 0, s>>>(work, tmp, side, n, mirror, z, p == 0 ? gain : 1.0);
+      zoom_cols_anticausal_kernel<<<cgrid, 128, 0, s>>>(tmp, work, side, n, mirror, z);
+    }
+    launch_counter() += 4 * npoles;
+  } else {
+    zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, (long long)side, 1LL, mirror, npoles, p0, p1);
+    zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, 1LL, (long long)side, mirror, npoles, p0, p1);
+    launch_counter() += 2;
+  }
   BP_CUDA_TRY(cudaGetLastError());
   return BP_OK;
 }
@@ -248,11 +439,11 @@ extern "C" int bp_zoom_tiles(int device, const float* plane, int plane_h, int pl
   if (n == 0) return BP_OK;
   BP_CUDA_TRY(cudaSetDevice(device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  double* work = zoom_workspace(device, (size_t)n * side * side);
-  BP_REQUIRE(work, BP_E_NOMEM, "zoom_tiles: %zu bytes of workspace", (size_t)n * side * side * sizeof(double));
+  double* work = zoom_workspace(device, 2 * (size_t)n * side * side);
+  BP_REQUIRE(work, BP_E_NOMEM, "zoom_tiles: %zu bytes of workspace", 2 * (size_t)n * side * side * sizeof(double));
   const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
   zoom_crop_kernel<float><<<dim3((side + 255) / 256, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
-  int rc = zoom_prefilter(work, side, n, 3, mirror, s);
+  int rc = zoom_prefilter(work, work + (size_t)n * side * side, side, n, 3, mirror, s);
   if (rc != BP_OK) return rc;
   zoom_eval_kernel<3, false><<<dim3((out_side + 127) / 128, out_side, n), 128, 0, s>>>(work, side, out_side, mirror, out, 1.0);
   launch_counter() += 2;
@@ -268,11 +459,11 @@ extern "C" int bp_zoom_accumulate(int device, const double* plane, int side, int
   BP_REQUIRE(mode == BP_ZOOM_REFLECT || mode == BP_ZOOM_MIRROR, BP_E_UNSUPPORTED, "zoom_accumulate: boundary mode %d", mode);
   BP_CUDA_TRY(cudaSetDevice(device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  double* work = zoom_workspace(device, (size_t)side * side);
-  BP_REQUIRE(work, BP_E_NOMEM, "zoom_accumulate: %zu bytes of workspace", (size_t)side * side * sizeof(double));
+  double* work = zoom_workspace(device, 2 * (size_t)side * side);
+  BP_REQUIRE(work, BP_E_NOMEM, "zoom_accumulate: %zu bytes of workspace", 2 * (size_t)side * side * sizeof(double));
   const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
   zoom_crop_kernel<double><<<dim3((side + 255) / 256, side, 1), 256, 0, s>>>(plane, side, side, nullptr, side, work);
-  int rc = zoom_prefilter(work, side, 1, order, mirror, s);
+  int rc = zoom_prefilter(work, work + (size_t)side * side, side, 1, order, mirror, s);
   if (rc != BP_OK) return rc;
   const dim3 grid((out_side + 127) / 128, out_side, 1);
   if (order == 3) zoom_eval_kernel<3, true><<<grid, 128, 0, s>>>(work, side, out_side, mirror, map, scale);

@@ -114,8 +114,10 @@ class DeviceBackend:
         with self._stage_lock:
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(self.device)
-            pinned = torch.empty(host.shape, dtype=getattr(torch, host.dtype.name), pin_memory=True)
-            pinned.numpy()[...] = host                      # (a file reader can fill `pinned` directly: read_into)
+            pinned = torch.from_numpy(host)
+            if not pinned.is_pinned():                      # (baryon_painter_b200.pinned_empty arrays are used in place)
+                pinned = torch.empty(host.shape, dtype=getattr(torch, host.dtype.name), pin_memory=True)
+                pinned.numpy()[...] = host
             with torch.cuda.stream(self._copy_stream):
                 dev = pinned.to(self.device, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -305,9 +307,9 @@ def _zoom(tile, n_pixel_tile, mode):
 # process_SLICS
 # ---------------------------------------------------------------------------------------------------
 def plan_planes(costs, world_size):
-    """Owner rank of every plane: longest-processing-time-first list scheduling of the per-plane costs (tiles to
-    paint: 1 for a mass plane, n^2 for a tiled delta plane -- 1, 1, 4, 9, ..., 144 for a SLICS line of sight,
-    reference process_SLICS.py:177-220).  Deterministic: ties go to the lower rank / lower plane index."""
+    """Owner rank of every plane: longest-processing-time-first list scheduling of the per-plane costs
+    (``plane_cost``; a SLICS line of sight has 1, 1, 4, 9, ..., 144 tiles per plane, reference
+    process_SLICS.py:177-220).  Deterministic: ties go to the lower rank / lower plane index."""
     owner, load = [0] * len(costs), [0.0] * max(1, world_size)
     for i in sorted(range(len(costs)), key=lambda k: (-costs[k], k)):
         r = min(range(len(load)), key=lambda q: (load[q], q))
@@ -323,6 +325,21 @@ def _plane_geometry(delta_size_i, tile_size, n_pixel_tile):
     n_pixel_plane = int(delta_size_i / tile_size * n_pixel_tile)
     origins, _ = generate_tiling(n_pixel_plane=n_pixel_plane, n_pixel_tile=n_pixel_tile, min_tile_overlap=0.5)
     return "delta", len(origins), n_pixel_plane
+
+
+def plane_cost(kind, tiles_per_side, delta_size_i, tile_size):
+    """Device seconds one slice costs its owner, for ``plan_planes``: painting is per tile (36 us on a B200); the tile
+    extraction runs the cubic-spline prefilter over every source pixel of every (overlapping) crop, 2.6e-11 s per crop
+    pixel (measured: 65 ms of a 131 ms line of sight, bench.py --config lightcone), which is nearly the same for
+    every delta plane however many tiles it is cut into; plus the upload of the plane itself."""
+    n = tiles_per_side ** 2
+    if kind == "mass":
+        side = N_PIXEL_MASSPLANE * delta_size_i / MASSPLANE_SIZE * (tile_size / delta_size_i)
+        upload = N_PIXEL_MASSPLANE ** 2 * 4 / 50e9
+    else:
+        side = N_PIXEL_DELTA * tile_size / delta_size_i
+        upload = N_PIXEL_DELTA ** 2 * 4 / 50e9
+    return n * (36e-6 + 2.6e-11 * side * side) + upload
 
 
 class _PlaneFeed:
@@ -365,16 +382,46 @@ class _PlaneFeed:
         return val
 
 
+class _StageClock:
+    """Optional per-stage wall clock of the lightcone loop (synchronises the device around every stage, so it is for
+    attribution runs only -- ``bench.py --config lightcone --stages``)."""
+
+    def __init__(self, sync):
+        self.t, self._sync = {}, sync
+
+    def __call__(self, name):
+        clock = self
+
+        class _Ctx:
+            def __enter__(self):
+                import time
+                clock._sync()
+                self.t0 = time.perf_counter()
+
+            def __exit__(self, *a):
+                import time
+                clock._sync()
+                clock.t[name] = clock.t.get(name, 0.0) + time.perf_counter() - self.t0
+        return _Ctx()
+
+
+class _NoClock:
+    def __call__(self, name):
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_slice, shift, SLICS_density, batch, say,
-                 tile_filter=None):
+                 tile_filter=None, clock=_NoClock()):
     """One lightcone slice -> its painted plane (backend array: device tensor / numpy, float64).  Mass-plane branch
     (reference :149-176): one tile, expanded crop, painted, cropped back.  Delta branch (:177-220): tiled, painted in
     batches, blended with the Gaussian-edge weights.  ``tile_filter(j, k)``: paint only those tiles (partial planes)."""
     if delta_size[i] < tile_size:
         say("  Extracting tile.")
         if hasattr(be, "extract_tiles") and not SLICS_density:
-            tile = be.extract_tiles(plane, [shift], delta_size[i] / MASSPLANE_SIZE, n_pixel_tile, "mirror",
-                                    expansion_factor=tile_size / delta_size[i])
+            with clock("extract"):
+                tile = be.extract_tiles(plane, [shift], delta_size[i] / MASSPLANE_SIZE, n_pixel_tile, "mirror",
+                                        expansion_factor=tile_size / delta_size[i])
         else:
             plane = be.to_host(plane)
             tile = get_tile(plane, shift=shift, tile_relative_size=delta_size[i] / MASSPLANE_SIZE,
@@ -383,7 +430,8 @@ def _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_s
                 tile = tile - tile.min()
             tile = _zoom(tile, n_pixel_tile, "mirror")[None]
         say("  Painting on tile.")
-        painted = be.paint(painter, tile, z_slice[i], batch)
+        with clock("paint"):
+            painted = be.paint(painter, tile, z_slice[i], batch)
         c = (1 - delta_size[i] / tile_size) / 2
         return be.crop(painted[0], shift=(c, c), tile_relative_size=delta_size[i] / tile_size), None
     n_pixel_plane = int(delta_size[i] / tile_size * n_pixel_tile)
@@ -405,17 +453,20 @@ def _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_s
             say(f"    Painting on tile {j + 1}-{k + 1}")
     if dest:
         if on_device:
-            tiles = be.extract_tiles(plane, shifts, tile_size / delta_size[i], n_pixel_tile, "reflect")
+            with clock("extract"):
+                tiles = be.extract_tiles(plane, shifts, tile_size / delta_size[i], n_pixel_tile, "reflect")
         else:
             tiles = np.stack(tiles).astype(np.float32, copy=False)
-        painted = be.paint(painter, tiles, z_slice[i], batch)
-        be.accumulate(planes, painted, dest, 0.05, 0.5)
+        with clock("paint"):
+            painted = be.paint(painter, tiles, z_slice[i], batch)
+        with clock("stitch"):
+            be.accumulate(planes, painted, dest, 0.05, 0.5)
     return None, planes
 
 
 def _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, delta_path, massplane_path, shifts_path,
                    z_slice, verbose, SLICS_density, regularise_std, plane_source, rank, world_size, batch, backend,
-                   on_plane):
+                   on_plane, clock=_NoClock()):
     """Shared driver of ``process_SLICS`` and ``paint_lightcone``: planes are dealt to the ranks whole (``plan_planes``),
     every rank loads ONLY its planes (one ahead, ``_PlaneFeed``), paints and stitches them on its device and calls
     ``on_plane(i, plane)`` with each finished float64 plane.  No collective in here."""
@@ -427,7 +478,7 @@ def _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, d
     be = backend if backend is not None else DeviceBackend(getattr(painter, "compute_device", None))
     say = print if (verbose and rank == 0) else (lambda *a, **k: None)
     geom = [_plane_geometry(delta_size[i], tile_size, n_pixel_tile) for i in range(len(z_SLICS))]
-    owner = plan_planes([g[1] ** 2 for g in geom], world_size)
+    owner = plan_planes([plane_cost(g[0], g[1], delta_size[i], tile_size) for i, g in enumerate(geom)], world_size)
     mine = [i for i in range(len(z_SLICS)) if owner[i] == rank]
     file_shifts = None
 
@@ -442,7 +493,8 @@ def _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, d
     feed = _PlaneFeed(mine, load)
     for i in mine:
         say(f"Processing z={z_SLICS[i]:.3f}")
-        plane = feed.get(i)
+        with clock("wait_plane"):
+            plane = feed.get(i)
         shift = None
         if geom[i][0] == "mass":
             say("  Tile bigger than delta plane, using mass planes.")
@@ -453,8 +505,9 @@ def _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, d
                     file_shifts = np.loadtxt(os.path.join(shifts_path, f"random_shift_LOS{LOS}"))[::-1]
                 shift = file_shifts[i]
         cropped, planes = _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_slice, shift,
-                                       SLICS_density, batch, say)
-        on_plane(i, cropped if planes is None else be.finalize_device(planes))
+                                       SLICS_density, batch, say, clock=clock)
+        with clock("project"):
+            on_plane(i, cropped if planes is None else be.finalize_device(planes))
         del plane
     return be, owner, geom
 
@@ -502,7 +555,8 @@ def process_SLICS(painter,
 
 def paint_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, delta_path, massplane_path, shifts_path,
                     z_slice, resolution, map_size, cosmo, order=5, verbose=True, SLICS_density=False, plane_source=None,
-                    rank=0, world_size=1, group=None, batch=64, backend=None, drop_planes=None, keep_planes=False):
+                    rank=0, world_size=1, group=None, batch=64, backend=None, drop_planes=None, keep_planes=False,
+                    stage_times=None):
     """``process_SLICS`` + ``create_y_map`` (reference scripts/create_lightcone.py:106-128) as one sharded pass:
     every rank paints and stitches its own planes and adds each, with the plane's physical prefactor, to ITS partial
     Compton-y map on its device (the projection is linear in the planes); ONE reduction of the ``resolution``^2
@@ -528,10 +582,16 @@ def paint_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, 
         if keep_planes:
             kept[i] = np.asarray(be.to_host(plane), np.float64)
 
+    clock = _NoClock()
+    if stage_times is not None and hasattr(be, "torch"):
+        clock = _StageClock(lambda: be.torch.cuda.synchronize(be.device))
     _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, delta_path, massplane_path, shifts_path,
-                   z_slice, verbose, SLICS_density, None, plane_source, rank, world_size, batch, be, on_plane)
+                   z_slice, verbose, SLICS_density, None, plane_source, rank, world_size, batch, be, on_plane, clock=clock)
     if world_size > 1:
-        maps = be.reduce(maps, 0, group)                    # the one collective of the run
+        with clock("reduce"):
+            maps = be.reduce(maps, 0, group)                # the one collective of the run
+    if stage_times is not None and isinstance(clock, _StageClock):
+        stage_times.update(clock.t)
     out = None
     if rank == 0:
         out = tuple(np.asarray(be.to_host(m), np.float64) for m in maps)

@@ -168,8 +168,114 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+def run_lightcone(args):
+    """BASELINE.json configs[4]: one full synthetic line of sight -- 15 lightcone slices (2 mass planes of 12288^2,
+    13 delta planes of 7745^2 pixels, 781 tiles of 512^2) tiled, painted, stitched and projected to a 1549^2 Compton-y
+    map (reference scripts/create_lightcone.py:106-128), planes dealt to the N ranks by cost, one NCCL reduction of
+    the map.  A step = one line of sight; planes are page-locked host arrays made before the timed region (the
+    stand-in for the SLICS files: disk reads are not timed, the host->device upload of every plane is)."""
+    import torch
+    import torch.distributed as dist
+    import baryon_painter_b200 as bp
+    from baryon_painter_b200 import process_SLICS as ps
+    from baryon_painter_b200.painter import CVAEPainter
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_z, h, tile_size, n_pixel_tile = args.planes, 0.6898, 100.0, TILE
+    cosmo = ps.FlatLCDM(Omega_m=0.2905, h=h)
+    chi = 252.5 / h * (np.arange(n_z) + 0.5)
+    z_SLICS = 1 / cosmo.scale_factor_of_chi(chi) - 1
+    delta_size = chi * h * 10 / 180 * np.pi
+    z_slice = np.array([1 / float(cosmo.scale_factor_of_chi(252.5 / h * i)) - 1 for i in range(n_z)])
+    shifts = np.random.default_rng(0).random((n_z, 2))
+    geom = [ps._plane_geometry(delta_size[i], tile_size, n_pixel_tile) for i in range(n_z)]
+    owner = ps.plan_planes([ps.plane_cost(g[0], g[1], delta_size[i], tile_size) for i, g in enumerate(geom)], world)
+    n_tiles = sum(g[1] ** 2 for g in geom)
+    scale = args.plane_scale              # 1.0 = the SLICS plane sizes
+    planes = {}
+    for i in range(n_z):                  # this rank's planes only, page-locked, block-constant log-normal densities
+        if owner[i] != rank:
+            continue
+        # smooth, strictly positive, periodic log-normal density (mean ~1): a 512^2 Gaussian-filtered field tiled up to
+        # the plane size (the cubic-spline resampling of a field with sharp edges overshoots below zero, and the
+        # shift-log transform of a negative density is NaN)
+        import scipy.ndimage
+        n = int((ps.N_PIXEL_MASSPLANE if geom[i][0] == "mass" else ps.N_PIXEL_DELTA) * scale)
+        g = scipy.ndimage.gaussian_filter(np.random.default_rng(100 + i).standard_normal((512, 512)), 3.0, mode="wrap")
+        base = np.exp(g / g.std() - 0.5).astype(np.float32)
+        reps = (n + 511) // 512
+        buf = bp.pinned_empty((n, n))
+        buf[...] = np.tile(base, (reps, reps))[:n, :n]
+        planes[i] = buf
+    painter = CVAEPainter.synthetic(tile_size=TILE, seed=0, compute_device="cuda:%d" % local, precision=args.precision,
+                                    max_batch=args.tiles)
+    be = ps.DeviceBackend("cuda:%d" % local)
+    kw = dict(tile_size=tile_size, n_pixel_tile=n_pixel_tile, LOS=0, z_SLICS=z_SLICS, delta_size=delta_size, delta_path=None,
+              massplane_path=None, shifts_path=shifts, z_slice=z_slice, resolution=1549, map_size=10.0, cosmo=cosmo, order=5,
+              verbose=False, plane_source=lambda i, kind: planes[i], rank=rank, world_size=world, batch=args.tiles, backend=be)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    y_map = None
+    for _ in range(max(1, args.warmup)):
+        y_map = ps.paint_lightcone(painter, **kw)
+    times = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib_launches = __import__("baryon_painter_b200._lib", fromlist=["x"])
+    _lib_launches.launch_count(reset=True)
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        y_map = ps.paint_lightcone(painter, **kw)
+        barrier()
+        times.append(time.perf_counter() - t0)
+    launches = _lib_launches.launch_count(reset=True)
+    clocks = sampler.stop()
+    stages = {}
+    ps.paint_lightcone(painter, stage_times=stages, **kw)          # one more pass with per-stage synchronised clocks
+    t = torch.tensor([float(np.median(times)), float(np.sum(times))], dtype=torch.float64, device="cuda")
+    st = torch.tensor([stages.get(k, 0.0) for k in ("wait_plane", "extract", "paint", "stitch", "project", "reduce")],
+                      dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        med, tot = float(t[0]), float(t[1])
+        assert y_map is not None and y_map.shape == (1549, 1549) and np.isfinite(y_map).all() and y_map.max() > 0, (np.isfinite(y_map).mean(), float(np.nanmax(y_map)))
+        loads = [sum(g[1] ** 2 for g, o in zip(geom, owner) if o == r) for r in range(world)]
+        print(json.dumps({
+            "metric": "lightcone lines of sight/sec (create_lightcone: %d planes, %d tiles -> 1549^2 y map)" % (n_z, n_tiles),
+            "value": 1.0 / med, "unit": "LOS/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+            "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"fp16": "f16", "bf16": "bf16"}.get(args.precision, args.precision), "data": "synthetic",
+            "tiles_per_s": n_tiles / med,
+            "config": {"workload": "full create_lightcone line of sight (BASELINE.json configs[4]): %d synthetic slices, "
+                                   "plane pixels x%.2f of SLICS (12288^2 mass / 7745^2 delta), %d tiles of 512^2, quintic "
+                                   "projection to 1549^2" % (n_z, scale, n_tiles),
+                       "parallelism": "whole planes dealt to %d rank(s) by cost (tiles per rank: %s), one NCCL reduce of "
+                                      "the 19 MB map" % (world, loads),
+                       "timed": "host wall clock between barriers + device synchronisation, max over ranks, median of "
+                                "%d lines of sight; plane uploads (page-locked) inside" % args.steps},
+            "stages_s_max_over_ranks": dict(zip(("wait_plane", "extract", "paint", "stitch", "project", "reduce"),
+                                                [float(v) for v in st])),
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="paint", help="paint (BASELINE configs[1], default) | lightcone (configs[4])")
+    ap.add_argument("--planes", type=int, default=15, help="lightcone: number of slices")
+    ap.add_argument("--plane-scale", type=float, default=1.0, help="lightcone: plane pixel count relative to SLICS")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -184,6 +290,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "lightcone":
+        if args.steps == 20:
+            args.steps = 3
+        return run_lightcone(args)
 
     import torch
     import torch.distributed as dist

@@ -105,3 +105,37 @@ def test_gpu_plane_prepare_bit_identical_to_numpy():
     t = ps.get_tile(delta, shift=(0.1, 0.8), tile_relative_size=0.4)
     ref = scipy.ndimage.zoom(t, zoom=64 / t.shape[0], mode="reflect")
     np.testing.assert_allclose(tiles[0].cpu().numpy(), ref, rtol=3e-6, atol=3e-6 * np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,side", [("reflect", 1357), ("mirror", 777), ("reflect", 513)])
+def test_gpu_zoom_long_lines_match_scipy(mode, side):
+    """Crops longer than 512 samples run the segment-parallel prefilter (csrc/bp_zoom.cu: truncated boundary sums,
+    256-sample segments warmed up over the recursion's horizon); same scipy parity as the sequential kernels."""
+    import scipy.ndimage
+    import torch
+    from baryon_painter_b200 import _lib
+    from baryon_painter_b200 import process_SLICS as ps
+    n = 1600
+    plane = np.tile(_field(400, 5), (4, 4))
+    dev = torch.device("cuda:0")
+    d_plane = torch.from_numpy(plane).to(dev)
+    shifts = [(0.0, 0.0), (0.7, 0.9)]
+    rel = side / n
+    assert int(n * rel) == side
+    org = torch.tensor([[int(n * a), int(n * b)] for a, b in shifts], dtype=torch.int32, device=dev)
+    out = torch.empty((2, 256, 256), dtype=torch.float32, device=dev)
+    _lib.zoom_tiles(0, d_plane.data_ptr(), n, n, org.data_ptr(), side, 2, 256, mode, out.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream)
+    got = out.cpu().numpy()
+    for t, sh in enumerate(shifts):
+        tile = ps.get_tile(plane, shift=sh, tile_relative_size=rel)
+        ref = scipy.ndimage.zoom(tile, zoom=256 / tile.shape[0], mode=mode)
+        np.testing.assert_allclose(got[t], ref, rtol=3e-6, atol=3e-6)
+    # quintic projection of a long plane (two poles: four out-of-place sweeps per axis)
+    p64 = plane[:side, :side].astype(np.float64)
+    y = torch.zeros((300, 300), dtype=torch.float64, device=dev)
+    d64 = torch.from_numpy(p64).to(dev)
+    _lib.zoom_accumulate(0, d64.data_ptr(), side, 300, 5, "mirror", 2.5, y.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    ref = 2.5 * scipy.ndimage.zoom(p64, zoom=300 / side, order=5, mode="mirror")
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-10, atol=1e-12)
