@@ -280,6 +280,14 @@ def _load_massplane(massplane_path, z, i, LOS, be=None):
     return fn, raw.T * np.float32(MASS_NORM)
 
 
+def _massplane_view(massplane_path, z, i, LOS):
+    """The mass plane as the reference indexes it (``raw[1:].reshape(12288, -1).T``, :157-158) WITHOUT reading the
+    file: a transposed view of a memory map, so that ``get_tile`` touches only the pages of its crop."""
+    fn = _massplane_file(massplane_path, z, i, LOS)
+    mm = np.memmap(fn, dtype=np.float32, mode="r", offset=4)
+    return mm.reshape(N_PIXEL_MASSPLANE, -1).T
+
+
 def _load_delta(delta_path, z, LOS, SLICS_density, be=None):
     """Delta plane (reference :187-189): 7745^2 float32, transposed, ``+= 96`` (mean of the mass plane), ``*= MASS_NORM``."""
     if SLICS_density:
@@ -335,11 +343,18 @@ def plane_cost(kind, tiles_per_side, delta_size_i, tile_size):
     n = tiles_per_side ** 2
     if kind == "mass":
         side = N_PIXEL_MASSPLANE * delta_size_i / MASSPLANE_SIZE * (tile_size / delta_size_i)
-        upload = N_PIXEL_MASSPLANE ** 2 * 4 / 50e9
+        upload = side * side * 4 / 50e9 + 10e-3            # the crop only; ~10 ms of host indexing to make it
     else:
         side = N_PIXEL_DELTA * tile_size / delta_size_i
         upload = N_PIXEL_DELTA ** 2 * 4 / 50e9
     return n * (36e-6 + 2.6e-11 * side * side) + upload
+
+
+class _MassCrop:
+    """the ``get_tile`` crop of a mass plane (reference :165-167), taken on the host before the upload"""
+
+    def __init__(self, tile):
+        self.tile = tile
 
 
 class _PlaneFeed:
@@ -418,7 +433,15 @@ def _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_s
     batches, blended with the Gaussian-edge weights.  ``tile_filter(j, k)``: paint only those tiles (partial planes)."""
     if delta_size[i] < tile_size:
         say("  Extracting tile.")
-        if hasattr(be, "extract_tiles") and not SLICS_density:
+        if isinstance(plane, _MassCrop):
+            # the periodic crop was taken on the host (only ~4 % of a 12288^2 mass plane is needed: 24 MB instead of
+            # 604 MB cross PCIe); the cubic-spline resampling runs on the device
+            if hasattr(be, "extract_tiles"):
+                with clock("extract"):
+                    tile = be.extract_tiles(plane.tile, [(0.0, 0.0)], 1.0, n_pixel_tile, "mirror")
+            else:
+                tile = _zoom(be.to_host(plane.tile), n_pixel_tile, "mirror")[None]
+        elif hasattr(be, "extract_tiles") and not SLICS_density:
             with clock("extract"):
                 tile = be.extract_tiles(plane, [shift], delta_size[i] / MASSPLANE_SIZE, n_pixel_tile, "mirror",
                                         expansion_factor=tile_size / delta_size[i])
@@ -480,14 +503,36 @@ def _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, d
     geom = [_plane_geometry(delta_size[i], tile_size, n_pixel_tile) for i in range(len(z_SLICS))]
     owner = plan_planes([plane_cost(g[0], g[1], delta_size[i], tile_size) for i, g in enumerate(geom)], world_size)
     mine = [i for i in range(len(z_SLICS)) if owner[i] == rank]
-    file_shifts = None
+
+    shifts_cache = []
+
+    def mass_shift(i):
+        if plane_source is not None:
+            return np.asarray(shifts_path)[i]
+        if not shifts_cache:
+            shifts_cache.append(np.loadtxt(os.path.join(shifts_path, f"random_shift_LOS{LOS}"))[::-1])
+        return shifts_cache[0][i]
 
     def load(i):
         kind = geom[i][0]
+        stage = be.stage if hasattr(be, "stage") else (lambda a: a)
+        if kind == "mass" and not SLICS_density:
+            # crop on the host, upload the crop (see _MassCrop)
+            if plane_source is not None:
+                plane = plane_source(i, kind)
+                if not isinstance(plane, np.ndarray):
+                    return plane                          # a device tensor: crop it where it is
+            else:
+                plane = _massplane_view(massplane_path, z_SLICS[i], i, LOS)
+            crop = get_tile(plane, shift=mass_shift(i), tile_relative_size=delta_size[i] / MASSPLANE_SIZE,
+                            expansion_factor=tile_size / delta_size[i])
+            if plane_source is None:
+                crop = crop * np.float32(MASS_NORM)       # the reference scales the whole plane first: same float32 products
+            return _MassCrop(stage(np.ascontiguousarray(crop, np.float32)))
         if plane_source is not None:
-            return be.stage(plane_source(i, kind)) if hasattr(be, "stage") else plane_source(i, kind)
+            return stage(plane_source(i, kind))
         if kind == "mass":
-            return _load_massplane(massplane_path, z_SLICS[i], i, LOS, be if not SLICS_density else None)[1]
+            return _load_massplane(massplane_path, z_SLICS[i], i, LOS, None)[1]
         return _load_delta(delta_path, z_SLICS[i], LOS, SLICS_density, be)[1]
 
     feed = _PlaneFeed(mine, load)
@@ -498,12 +543,7 @@ def _run_lightcone(painter, tile_size, n_pixel_tile, LOS, z_SLICS, delta_size, d
         shift = None
         if geom[i][0] == "mass":
             say("  Tile bigger than delta plane, using mass planes.")
-            if plane_source is not None:
-                shift = np.asarray(shifts_path)[i]
-            else:
-                if file_shifts is None:
-                    file_shifts = np.loadtxt(os.path.join(shifts_path, f"random_shift_LOS{LOS}"))[::-1]
-                shift = file_shifts[i]
+            shift = mass_shift(i)
         cropped, planes = _paint_plane(i, plane, painter, be, tile_size, n_pixel_tile, delta_size, z_slice, shift,
                                        SLICS_density, batch, say, clock=clock)
         with clock("project"):

@@ -168,7 +168,7 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
-def run_lightcone(args):
+def measure_lightcone(args, rank, world, local, precision):
     """BASELINE.json configs[4]: one full synthetic line of sight -- 15 lightcone slices (2 mass planes of 12288^2,
     13 delta planes of 7745^2 pixels, 781 tiles of 512^2) tiled, painted, stitched and projected to a 1549^2 Compton-y
     map (reference scripts/create_lightcone.py:106-128), planes dealt to the N ranks by cost, one NCCL reduction of
@@ -179,12 +179,6 @@ def run_lightcone(args):
     import baryon_painter_b200 as bp
     from baryon_painter_b200 import process_SLICS as ps
     from baryon_painter_b200.painter import CVAEPainter
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_z, h, tile_size, n_pixel_tile = args.planes, 0.6898, 100.0, TILE
     cosmo = ps.FlatLCDM(Omega_m=0.2905, h=h)
     chi = 252.5 / h * (np.arange(n_z) + 0.5)
@@ -211,7 +205,7 @@ def run_lightcone(args):
         buf = bp.pinned_empty((n, n))
         buf[...] = np.tile(base, (reps, reps))[:n, :n]
         planes[i] = buf
-    painter = CVAEPainter.synthetic(tile_size=TILE, seed=0, compute_device="cuda:%d" % local, precision=args.precision,
+    painter = CVAEPainter.synthetic(tile_size=TILE, seed=0, compute_device="cuda:%d" % local, precision=precision,
                                     max_batch=args.tiles)
     be = ps.DeviceBackend("cuda:%d" % local)
     kw = dict(tile_size=tile_size, n_pixel_tile=n_pixel_tile, LOS=0, z_SLICS=z_SLICS, delta_size=delta_size, delta_path=None,
@@ -224,14 +218,15 @@ def run_lightcone(args):
         torch.cuda.synchronize()
 
     y_map = None
-    for _ in range(max(1, args.warmup)):
+    lc_steps = max(1, min(args.steps, 3)) if args.config != "lightcone" else args.steps
+    for _ in range(max(1, min(args.warmup, 1 if args.config != "lightcone" else args.warmup))):
         y_map = ps.paint_lightcone(painter, **kw)
     times = []
     sampler = ClockSampler(local)
     sampler.start()
     _lib_launches = __import__("baryon_painter_b200._lib", fromlist=["x"])
     _lib_launches.launch_count(reset=True)
-    for _ in range(args.steps):
+    for _ in range(lc_steps):
         barrier()
         t0 = time.perf_counter()
         y_map = ps.paint_lightcone(painter, **kw)
@@ -247,26 +242,42 @@ def run_lightcone(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    med = float(t[0])
+    assert y_map is not None and y_map.shape == (1549, 1549) and np.isfinite(y_map).all() and y_map.max() > 0, \
+        (np.isfinite(y_map).mean(), float(np.nanmax(y_map)))
+    loads = [sum(g[1] ** 2 for g, o in zip(geom, owner) if o == r) for r in range(world)]
+    return {
+        "metric": "lightcone lines of sight/sec (create_lightcone: %d planes, %d tiles -> 1549^2 y map)" % (n_z, n_tiles),
+        "value": 1.0 / med, "unit": "LOS/s", "n_gpus": world, "steps": lc_steps, "warmup": 1,
+        "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": {"fp16": "f16", "bf16": "bf16"}.get(precision, precision), "data": "synthetic",
+        "tiles_per_s": n_tiles / med,
+        "config": {"workload": "full create_lightcone line of sight (BASELINE.json configs[4]): %d synthetic slices, "
+                               "plane pixels x%.2f of SLICS (12288^2 mass / 7745^2 delta), %d tiles of 512^2, quintic "
+                               "projection to 1549^2" % (n_z, scale, n_tiles),
+                   "parallelism": "whole planes dealt to %d rank(s) by cost (tiles per rank: %s), one NCCL reduce of "
+                                  "the 19 MB map" % (world, loads),
+                   "timed": "host wall clock between barriers + device synchronisation, max over ranks, median of "
+                            "%d lines of sight; plane uploads (page-locked) inside" % lc_steps},
+        "stages_s_max_over_ranks": dict(zip(("wait_plane", "extract", "paint", "stitch", "project", "reduce"),
+                                            [float(v) for v in st])),
+        "gpu_launches": int(launches), "clocks": clocks}
+
+
+def run_lightcone(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure_lightcone(args, rank, world, local, args.precision)
     if rank == 0:
-        med, tot = float(t[0]), float(t[1])
-        assert y_map is not None and y_map.shape == (1549, 1549) and np.isfinite(y_map).all() and y_map.max() > 0, (np.isfinite(y_map).mean(), float(np.nanmax(y_map)))
-        loads = [sum(g[1] ** 2 for g, o in zip(geom, owner) if o == r) for r in range(world)]
-        print(json.dumps({
-            "metric": "lightcone lines of sight/sec (create_lightcone: %d planes, %d tiles -> 1549^2 y map)" % (n_z, n_tiles),
-            "value": 1.0 / med, "unit": "LOS/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
-            "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"fp16": "f16", "bf16": "bf16"}.get(args.precision, args.precision), "data": "synthetic",
-            "tiles_per_s": n_tiles / med,
-            "config": {"workload": "full create_lightcone line of sight (BASELINE.json configs[4]): %d synthetic slices, "
-                                   "plane pixels x%.2f of SLICS (12288^2 mass / 7745^2 delta), %d tiles of 512^2, quintic "
-                                   "projection to 1549^2" % (n_z, scale, n_tiles),
-                       "parallelism": "whole planes dealt to %d rank(s) by cost (tiles per rank: %s), one NCCL reduce of "
-                                      "the 19 MB map" % (world, loads),
-                       "timed": "host wall clock between barriers + device synchronisation, max over ranks, median of "
-                                "%d lines of sight; plane uploads (page-locked) inside" % args.steps},
-            "stages_s_max_over_ranks": dict(zip(("wait_plane", "extract", "paint", "stitch", "project", "reduce"),
-                                                [float(v) for v in st])),
-            "gpu_launches": int(launches), "clocks": clocks}))
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -286,6 +297,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed batch")
     ap.add_argument("--no-fp32", action="store_true", help="skip the secondary fp32-accurate measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the CGAN / variance-map / lightcone secondary fields")
+    ap.add_argument("--no-lightcone", action="store_true", help="skip the lightcone secondary field")
     ap.add_argument("--profile-layers", action="store_true", help="print the per-layer timing table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -479,6 +492,66 @@ def main():
             raise RuntimeError("fp32 parity of the benchmarked batch failed: %r" % (fp32,))
         del p32, net32
 
+    # ---- the other BASELINE.json configurations as secondary, driver-visible fields (N = 1 only)
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        from baryon_painter_b200.painter import CGANPainter
+        # configs[2]: CGAN generator, 256 tiles, z cycling over {0, 0.5, 1} (100.7 GFLOP per tile)
+        nc = min(n, 256)
+        g = CGANPainter.synthetic(tile_size=TILE, seed=0, device="cuda:%d" % local, precision=args.precision, max_batch=nc)
+        zc = np.array([0.0, 0.5, 1.0])[np.arange(nc) % 3]
+        uz, inv = np.unique(zc, return_inverse=True)
+        pin = [g.transform.gpu_params("dm", float(v)) for v in uz]
+        pout = [g.inverse_transform.gpu_params("pressure", float(v)) for v in uz]
+        tpc = (np.array([q[1] for q in pin], np.float32)[inv], np.array([q[1] for q in pout], np.float32)[inv],
+               (zc - g.z_shift).astype(np.float32), pin[0][2], pin[0][3], pout[0][2], pout[0][3])
+        d_outc = torch.empty((nc, TILE, TILE), dtype=torch.float32, device="cuda")
+
+        def stepc():
+            g.model.net.cgan_paint_device(d_tiles.data_ptr(), tpc, flags, d_outc.data_ptr(), nc, stream)
+        for _ in range(3):
+            stepc()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kc = 5
+        c0.record()
+        for _ in range(kc):
+            stepc()
+        c1.record()
+        torch.cuda.synchronize()
+        msc = c0.elapsed_time(c1) / kc
+        par = None
+        if not args.no_parity:
+            from oracle.cvae_oracle import CGANOracle
+            from baryon_painter_b200 import arch as _arch
+            layers = _arch.fiducial_cgan_architecture()
+            corc = CGANOracle(layers, synthetic.synthetic_cgan_state_dict(layers, seed=0))
+            errs = []
+            for i in (0, nc - 1):
+                ref = corc.paint(tiles_h[i], float(zc[i]), stats).astype(np.float64)
+                got = d_outc[i].cpu().numpy().astype(np.float64)
+                errs.append(float(np.sqrt(((got - ref) ** 2).sum() / (ref ** 2).sum())))
+            par = {"tiles": 2, "max_rel_l2": max(errs), "tol": 1e-2, "ok": bool(max(errs) <= 1e-2),
+                   "oracle": "restatement of trained_models/README.md + g_struc.pickle (parity unpinned: no PainterGAN source)"}
+        extra["cgan"] = {"value": nc / (msc * 1e-3), "unit": "tiles/s", "ms_per_step": msc, "tiles": nc, "z": [0.0, 0.5, 1.0],
+                         "flops_per_tile": 100.7e9, "frac_of_bf16_roofline": nc / (msc * 1e-3) * 100.7e9 / 1e12 / pk["bf16_tflops"],
+                         "parity": par}
+        del g, d_outc
+        # configs[3]: 64 latent draws per tile -> per-pixel mean / variance maps (host buffers)
+        nv, nd = 16, 64
+        painter.paint_variance(tiles_h[:nv], z=0.0, n_draws=4, seed=1)
+        t0 = time.perf_counter()
+        mean_v, var_v = painter.paint_variance(tiles_h[:nv], z=0.0, n_draws=nd, seed=1)
+        dtv = time.perf_counter() - t0
+        extra["variance"] = {"value": nv * nd / dtv, "unit": "draws/s", "tiles": nv, "draws_per_tile": nd,
+                             "finite": bool(np.isfinite(mean_v).all() and (var_v >= 0).all()),
+                             "note": "host tiles in, mean / variance maps out; parity vs oracle draws: tests/test_gpu_cvae.py"}
+        # configs[4]: one full synthetic line of sight on this GPU
+        if not args.no_lightcone:
+            del painter
+            lc = measure_lightcone(args, 0, 1, local, args.precision)
+            extra["lightcone"] = {k: lc[k] for k in ("metric", "value", "unit", "ms_per_step", "tiles_per_s", "stages_s_max_over_ranks")}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt = cpu_baseline(args.cpu_tiles, os.cpu_count())
@@ -495,7 +568,7 @@ def main():
             "config": workload_config(n, world),
             "e2e": {"value": total_tiles / (e2e_ms * 1e-3), "unit": "tiles/s",
                     "h2d_bytes_per_step": int(tiles_h.nbytes + eps_h.nbytes), "d2h_bytes_per_step": int(out_h.nbytes)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "fp32": fp32}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "fp32": fp32, **extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
