@@ -425,14 +425,15 @@ int launch_front_latent(const float* tiles, const float* latent, const ActDesc& 
 }
 
 // ---- tail: 1 -> 1 channel k x k convolution (fp32) + activation + inverse transform ------------------
-// CTA = 64 x 16 outputs, 4 along x per thread.  The shared tile keeps the image column x0 at a 16-byte aligned
-// offset (4 floats in), so a thread's window is one float4 plus R scalars either side per row.
+// CTA = 64 x 64 outputs (four 16-row passes over one shared window: a quarter of the CTAs, halo rows and barriers of
+// a 64 x 16 tile), 4 along x per thread.  The shared tile keeps the image column x0 at a 16-byte aligned offset
+// (4 floats in), so a thread's window is one float4 plus R scalars either side per row.
 template <int K>
 __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            long long out_bs, const TailParams tp,
                                                            const float* __restrict__ post_sigma, int H, int W) {
   constexpr int R = K / 2;
-  constexpr int TX = 64, TY = 16, SW = TX + 8;      // row stride 72 floats: offset 4 + [-R, TX + R)
+  constexpr int TX = 64, TY = 64, SW = TX + 8;      // row stride 72 floats: offset 4 + [-R, TX + R)
   static_assert(R <= 4, "halo must fit the 4-float margins");
   __shared__ __align__(16) float sh[TY + 2 * R][SW];
   const int n = blockIdx.z;
@@ -461,57 +462,60 @@ __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restri
     }
   }
   __syncthreads();
-  const int ty = threadIdx.x / 16, tx = (threadIdx.x % 16) * 4;
-  const int y = y0 + ty;
-  if (y >= H) return;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int r = 0; r < K; ++r) {
-    float v[4 + 2 * R];
-    const float4 c4 = *reinterpret_cast<const float4*>(&sh[ty + r][4 + tx]);
-    v[R] = c4.x; v[R + 1] = c4.y; v[R + 2] = c4.z; v[R + 3] = c4.w;
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-      v[q] = sh[ty + r][4 + tx - R + q];
-      v[R + 4 + q] = sh[ty + r][4 + tx + 4 + q];
-    }
-#pragma unroll
-    for (int q = 0; q < K; ++q) {
-      const float w = tp.w[r * K + q];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] = fmaf(v[e + q], w, acc[e]);
-    }
-  }
+  const int tx = (threadIdx.x % 16) * 4;
   const float sg = tp.post ? post_sigma[n] : 1.f;
-  float o[4];
+#pragma unroll 1
+  for (int ty = threadIdx.x / 16; ty < TY; ty += 16) {
+    const int y = y0 + ty;
+    if (y >= H) break;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float v = fmaf(acc[e], tp.scale, tp.shift);
-    if (tp.precise) {
-      // fp32-accurate path: the library functions (<= 2 ulp), as the reference's torch / numpy float32 arithmetic
-      v = f_act(v, tp.act, tp.act_param);
-      if (tp.post) v = (expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
-    } else {
-      // 16-bit path: fast exp / log (a few ulp) are far below its tolerance
-      if (tp.act == BP_ACT_SOFTPLUS) v = v > 20.f ? v : __logf(1.f + __expf(v));
-      else v = f_act(v, tp.act, tp.act_param);
-      if (tp.post) v = (__expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+    for (int r = 0; r < K; ++r) {
+      float v[4 + 2 * R];
+      const float4 c4 = *reinterpret_cast<const float4*>(&sh[ty + r][4 + tx]);
+      v[R] = c4.x; v[R + 1] = c4.y; v[R + 2] = c4.z; v[R + 3] = c4.w;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        v[q] = sh[ty + r][4 + tx - R + q];
+        v[R + 4 + q] = sh[ty + r][4 + tx + 4 + q];
+      }
+#pragma unroll
+      for (int q = 0; q < K; ++q) {
+        const float w = tp.w[r * K + q];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = fmaf(v[e + q], w, acc[e]);
+      }
     }
-    o[e] = v;
-  }
-  float* dst = out + (size_t)n * out_bs + (size_t)y * W + x0 + tx;
-  if (x0 + tx + 3 < W && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-  } else {
+    float o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (x0 + tx + e < W) dst[e] = o[e];
+    for (int e = 0; e < 4; ++e) {
+      float v = fmaf(acc[e], tp.scale, tp.shift);
+      if (tp.precise) {
+        // fp32-accurate path: the library functions (<= 2 ulp), as the reference's torch / numpy float32 arithmetic
+        v = f_act(v, tp.act, tp.act_param);
+        if (tp.post) v = (expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+      } else {
+        // 16-bit path: fast exp / log (a few ulp) are far below its tolerance
+        if (tp.act == BP_ACT_SOFTPLUS) v = v > 20.f ? v : __logf(1.f + __expf(v));
+        else v = f_act(v, tp.act, tp.act_param);
+        if (tp.post) v = (__expf((v + tp.post_shift) * tp.post_k) - 1.f) * sg;
+      }
+      o[e] = v;
+    }
+    float* dst = out + (size_t)n * out_bs + (size_t)y * W + x0 + tx;
+    if (x0 + tx + 3 < W && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (x0 + tx + e < W) dst[e] = o[e];
+    }
   }
 }
 
 int launch_tail_stencil(const float* in, float* out, long long out_bs, const TailParams& tp, const float* post_sigma, int H,
                         int W, int nb, cudaStream_t s) {
-  const dim3 grid((W + 63) / 64, (H + 15) / 16, nb);
+  const dim3 grid((W + 63) / 64, (H + 63) / 64, nb);
   switch (tp.k) {
     case 1: tail_stencil_kernel<1><<<grid, 256, 0, s>>>(in, out, out_bs, tp, post_sigma, H, W); break;
     case 3: tail_stencil_kernel<3><<<grid, 256, 0, s>>>(in, out, out_bs, tp, post_sigma, H, W); break;

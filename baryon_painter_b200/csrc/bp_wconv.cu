@@ -229,7 +229,9 @@ __device__ __forceinline__ WRegion w_decode(const WArgs& a, int reg) {
 //   * with NI = 2 two warps issue, each for every other M-tile of the region (its own accumulators): a
 //     UTCHMMA blocks its issuing thread until the tensor pipe takes it, so one warp's descriptor arithmetic and
 //     barrier handshakes run while the other warp's MMA executes; both commit to every barrier (count NI)
-template <int T_R, int NI, int H>
+// MACC: the split-precision layers spread a region's MMAs over several accumulators (index in bits [20, 24) of the
+// slot table); the plain 16-bit layers keep the single-accumulator loop, whose bookkeeping stays on the uniform datapath
+template <int T_R, int NI, int H, bool MACC>
 __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB, uint64_t* bars, uint32_t tmem_base,
                                         long long* tacc) {
   uint64_t* full_p = bars;
@@ -284,12 +286,22 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
 #pragma unroll 2
         for (int sl = 0; sl < ns1; ++sl) {
           const uint32_t ao = a.aoff[sbase + s0 + sl];               // [0, 20): A offset; [20, 24): accumulator
-          const uint32_t da = da_blk + (ao & 0xFFFFFu), ci = ao >> 20;
-          const uint32_t acc = (used >> ci) & 1u, dt = d_tmem + ci * acc_stride;
+          uint32_t da, acc, dt;
+          if (MACC) {
+            const uint32_t ci = ao >> 20;
+            da = da_blk + (ao & 0xFFFFFu);
+            acc = (used >> ci) & 1u;
+            dt = d_tmem + ci * acc_stride;
+            used |= 1u << ci;
+          } else {
+            da = da_blk + ao;
+            acc = used;
+            dt = d_tmem;
+            used = 1u;
+          }
 #pragma unroll
           for (int mt = H; mt < T_R; mt += NI)
             umma_f16_lohi(dt + (uint32_t)(mt * N), da + (uint32_t)mt * tile_step16, a_hi, db, b_hi, idesc, acc, el);
-          used |= 1u << ci;
           db += bstep16;
         }
         // probe the next weight stage's barrier now and look at the answer after the last few slots: when the data
@@ -305,12 +317,22 @@ __device__ __forceinline__ void w_issue(const WArgs& a, uint8_t* sP, uint8_t* sB
 #pragma unroll 2
         for (int sl = ns1; sl < ns; ++sl) {
           const uint32_t ao = a.aoff[sbase + s0 + sl];               // [0, 20): A offset; [20, 24): accumulator
-          const uint32_t da = da_blk + (ao & 0xFFFFFu), ci = ao >> 20;
-          const uint32_t acc = (used >> ci) & 1u, dt = d_tmem + ci * acc_stride;
+          uint32_t da, acc, dt;
+          if (MACC) {
+            const uint32_t ci = ao >> 20;
+            da = da_blk + (ao & 0xFFFFFu);
+            acc = (used >> ci) & 1u;
+            dt = d_tmem + ci * acc_stride;
+            used |= 1u << ci;
+          } else {
+            da = da_blk + ao;
+            acc = used;
+            dt = d_tmem;
+            used = 1u;
+          }
 #pragma unroll
           for (int mt = H; mt < T_R; mt += NI)
             umma_f16_lohi(dt + (uint32_t)(mt * N), da + (uint32_t)mt * tile_step16, a_hi, db, b_hi, idesc, acc, el);
-          used |= 1u << ci;
           db += bstep16;
         }
         if (a.timing) tacc[3] += clock64() - t_loop;
@@ -424,16 +446,16 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     // ===================== MMA issuer =====================
     if (a.nissue == 2) {
       switch (a.T_r) {
-        case 2: w_issue<2, 2, 0>(a, sP, sB, bars, tmem_base, tacc); break;
-        case 3: w_issue<3, 2, 0>(a, sP, sB, bars, tmem_base, tacc); break;
-        default: w_issue<4, 2, 0>(a, sP, sB, bars, tmem_base, tacc); break;
+        case 2: w_issue<2, 2, 0, SPLIT>(a, sP, sB, bars, tmem_base, tacc); break;
+        case 3: w_issue<3, 2, 0, SPLIT>(a, sP, sB, bars, tmem_base, tacc); break;
+        default: w_issue<4, 2, 0, SPLIT>(a, sP, sB, bars, tmem_base, tacc); break;
       }
     } else {
       switch (a.T_r) {
-        case 1: w_issue<1, 1, 0>(a, sP, sB, bars, tmem_base, tacc); break;
-        case 2: w_issue<2, 1, 0>(a, sP, sB, bars, tmem_base, tacc); break;
-        case 3: w_issue<3, 1, 0>(a, sP, sB, bars, tmem_base, tacc); break;
-        default: w_issue<4, 1, 0>(a, sP, sB, bars, tmem_base, tacc); break;
+        case 1: w_issue<1, 1, 0, SPLIT>(a, sP, sB, bars, tmem_base, tacc); break;
+        case 2: w_issue<2, 1, 0, SPLIT>(a, sP, sB, bars, tmem_base, tacc); break;
+        case 3: w_issue<3, 1, 0, SPLIT>(a, sP, sB, bars, tmem_base, tacc); break;
+        default: w_issue<4, 1, 0, SPLIT>(a, sP, sB, bars, tmem_base, tacc); break;
       }
     }
   } else if (warp == 3) {
@@ -441,9 +463,9 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     if (a.nissue == 2) {
       long long tdummy[4] = {0, 0, 0, 0};
       switch (a.T_r) {
-        case 2: w_issue<2, 2, 1>(a, sP, sB, bars, tmem_base, tdummy); break;
-        case 3: w_issue<3, 2, 1>(a, sP, sB, bars, tmem_base, tdummy); break;
-        default: w_issue<4, 2, 1>(a, sP, sB, bars, tmem_base, tdummy); break;
+        case 2: w_issue<2, 2, 1, SPLIT>(a, sP, sB, bars, tmem_base, tdummy); break;
+        case 3: w_issue<3, 2, 1, SPLIT>(a, sP, sB, bars, tmem_base, tdummy); break;
+        default: w_issue<4, 2, 1, SPLIT>(a, sP, sB, bars, tmem_base, tdummy); break;
       }
     }
   } else if (warp >= 4) {

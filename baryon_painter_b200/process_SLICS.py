@@ -38,14 +38,24 @@ MASS_NORM = 1 / (3072 ** 3 / 2 / 12288 ** 2)
 # ---------------------------------------------------------------------------------------------------
 def get_tile(m, shift, tile_relative_size, expansion_factor=1):
     """Periodic crop of ``m`` (reference :68-83): origin ``int(n*shift)``, side
-    ``int(n*tile_relative_size*expansion_factor)``, centred expansion, wrap-around indexing."""
+    ``int(n*tile_relative_size*expansion_factor)``, centred expansion, wrap-around indexing.  A crop that wraps at
+    most once per axis is assembled from (up to four) contiguous slices -- the same elements as the reference's
+    ``take(..., mode="wrap")``, without a gather over a 600 MB plane."""
     if expansion_factor < 1:
         raise ValueError("Expension factors < 1 not supported.")
     n = m.shape[0]
     side = int(n * tile_relative_size * expansion_factor)
     pad = int(n * tile_relative_size * (expansion_factor - 1) / 2)
-    rows = (int(n * shift[0]) - pad + np.arange(side)) % m.shape[0]
-    cols = (int(n * shift[1]) - pad + np.arange(side)) % m.shape[1]
+    r0 = (int(n * shift[0]) - pad) % m.shape[0]
+    c0 = (int(n * shift[1]) - pad) % m.shape[1]
+    if side <= m.shape[0] and side <= m.shape[1]:
+        rs = [(r0, min(m.shape[0], r0 + side))] + ([(0, r0 + side - m.shape[0])] if r0 + side > m.shape[0] else [])
+        cs = [(c0, min(m.shape[1], c0 + side))] + ([(0, c0 + side - m.shape[1])] if c0 + side > m.shape[1] else [])
+        if len(rs) == 1 and len(cs) == 1:
+            return np.array(m[rs[0][0]:rs[0][1], cs[0][0]:cs[0][1]])
+        return np.block([[m[a:b, c:d] for c, d in cs] for a, b in rs])
+    rows = (r0 + np.arange(side)) % m.shape[0]
+    cols = (c0 + np.arange(side)) % m.shape[1]
     return m[np.ix_(rows, cols)]
 
 

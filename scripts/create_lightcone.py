@@ -155,28 +155,39 @@ if __name__ == "__main__":
 
     import time
     t_start = time.perf_counter()
-    painted_planes = baryon_painter_b200.process_SLICS.process_SLICS(
-        painter, tile_size=100.0, n_pixel_tile=512, LOS=LOS,
-        z_SLICS=z_SLICS[:n_z], delta_size=d_A_SLICS[:n_z] * 10 / 180 * pi,
-        delta_path=delta_path, massplane_path=massplane_path, shifts_path=shifts_path,
-        z_slice=z_slice[:n_z], min_tiling_overlap=tile_overlap, regularise=False, regularise_std=None,
-        verbose=rank == 0, plane_source=plane_source, rank=rank, world_size=world, batch=batch)
-
-    t_painted = time.perf_counter()
-    say(f"Painted and stitched {n_z} planes on {world} GPU(s) in {t_painted - t_start:.2f} s.")
-    if rank == 0:
-        output_resolution = int(args.output_resolution)
-        create_y_map = baryon_painter_b200.process_SLICS.create_y_map
-        be = baryon_painter_b200.process_SLICS.DeviceBackend(device)       # quintic zoom + sum on the GPU
-        y_map = create_y_map(painted_planes, z_SLICS[:n_z], resolution=output_resolution, map_size=10.0,
-                             cosmo=cosmo_SLICS, order=5, backend=be)
-        np.save(output_file, y_map)
-        say(f"Projected the y map ({output_resolution} px) in {time.perf_counter() - t_painted:.2f} s.")
-        if n_drop is not None:
-            y_map = create_y_map(painted_planes[n_drop:], z_SLICS[n_drop:n_z], resolution=output_resolution,
-                                 map_size=10.0, cosmo=cosmo_SLICS, order=5, backend=be)
-            np.save(output_file_drop, y_map)
-        if args.output_file_planes is not None:
+    ps = baryon_painter_b200.process_SLICS
+    common = dict(tile_size=100.0, n_pixel_tile=512, LOS=LOS, z_SLICS=z_SLICS[:n_z],
+                  delta_size=d_A_SLICS[:n_z] * 10 / 180 * pi, delta_path=delta_path, massplane_path=massplane_path,
+                  shifts_path=shifts_path, z_slice=z_slice[:n_z], verbose=rank == 0, plane_source=plane_source, rank=rank,
+                  world_size=world, batch=batch)
+    output_resolution = int(args.output_resolution)
+    if args.output_file_planes is None:
+        # the planes themselves are not wanted: every rank projects its own planes into its partial y map on its GPU
+        # and ONE reduction of the map assembles the result (reference :106-128 as a single sharded pass)
+        res = ps.paint_lightcone(painter, resolution=output_resolution, map_size=10.0, cosmo=cosmo_SLICS, order=5,
+                                 drop_planes=n_drop, **common)
+        say(f"Painted, stitched and projected {n_z} planes on {world} GPU(s) in {time.perf_counter() - t_start:.2f} s.")
+        if rank == 0:
+            if n_drop is None:
+                np.save(output_file, res)
+            else:
+                np.save(output_file, res[0])
+                np.save(output_file_drop, res[1])
+    else:
+        painted_planes = ps.process_SLICS(painter, min_tiling_overlap=tile_overlap, regularise=False, regularise_std=None,
+                                          **common)
+        t_painted = time.perf_counter()
+        say(f"Painted and stitched {n_z} planes on {world} GPU(s) in {t_painted - t_start:.2f} s.")
+        if rank == 0:
+            be = ps.DeviceBackend(device)       # quintic zoom + sum on the GPU
+            y_map = ps.create_y_map(painted_planes, z_SLICS[:n_z], resolution=output_resolution, map_size=10.0,
+                                    cosmo=cosmo_SLICS, order=5, backend=be)
+            np.save(output_file, y_map)
+            say(f"Projected the y map ({output_resolution} px) in {time.perf_counter() - t_painted:.2f} s.")
+            if n_drop is not None:
+                y_map = ps.create_y_map(painted_planes[n_drop:], z_SLICS[n_drop:n_z], resolution=output_resolution,
+                                        map_size=10.0, cosmo=cosmo_SLICS, order=5, backend=be)
+                np.save(output_file_drop, y_map)
             import pickle
             with open(args.output_file_planes, "wb") as f:
                 pickle.dump(painted_planes, f)
