@@ -884,6 +884,7 @@ static int v2_run(bp_net* net, std::vector<V2Op>& ops, float* final_out, long lo
                   cudaStream_t s) {
   V2Plan& P = net->v2;
   const int fmt = net->prec == BP_PREC_BF16 ? TC_FMT_BF16 : TC_FMT_F16;
+  int n_wconv = 0;
   for (V2Op& op : ops) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool layer_op = op.index >= 0;
@@ -904,7 +905,9 @@ static int v2_run(bp_net* net, std::vector<V2Op>& ops, float* final_out, long lo
         break;
       }
       case V2_WCONV:
-        rc = wconv_launch(op.w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, nb, s);
+        // alternate directions along the chain (the first layer runs in reverse: its producer, a front kernel or a
+        // layout conversion, walks the tiles forward)
+        rc = wconv_launch(op.w, P.acts[op.out], op.skip >= 0 ? P.acts[op.skip].ptr : nullptr, nb, s, (n_wconv++ & 1) == 0);
         break;
       case V2_COPY_F32: {
         const ActDesc& o = P.acts[op.out];

@@ -66,6 +66,7 @@ struct WArgs {
   int kb_slot0[W_MAX_KB], kb_nslots[W_MAX_KB], kb_spb[W_MAX_KB];
   int stages_per_phase;        // sum of kb_spb
   float acc_scale, out_scale, skip_scale;   // split precision: v = act(acc * acc_scale + shift + skip * skip_scale) * out_scale
+  int reverse;                 // walk the regions from the last to the first (see wconv_launch)
   int nacc, nbuf;              // accumulators per M-tile (split precision: short chains, summed to nearest in the
                                // epilogue) and accumulator buffers (2: the epilogue of region r overlaps the MMAs of r + 1)
   int split_off;               // split-precision output: element offset of a pixel's lo part (= Cp of the output), else 0
@@ -182,6 +183,7 @@ struct WRegion {
 // MMA issuers' critical path: divisions by multiply-high with host-made reciprocals (exact, range-checked there)
 __device__ __forceinline__ WRegion w_decode(const WArgs& a, int reg) {
   WRegion R;
+  if (a.reverse) reg = a.total_regions - 1 - reg;
   const int per_img = a.nstrips * a.regs_per_strip;
   const int per_phase = per_img * a.nb;
   R.pi = (reg >= per_phase) + (reg >= 2 * per_phase) + (reg >= 3 * per_phase);       // <= 4 phases
@@ -1199,7 +1201,10 @@ static WKernel pick_kernel(int act, bool skip, int f32, int fmt, bool split) {
 
 static int g_w_sms = 0;
 
-int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb, cudaStream_t s) {
+// reverse: process the regions (tiles) in descending order.  Consecutive layers of a chain alternate directions, so
+// that a layer starts with the tiles its producer wrote last -- the ~100 MB of them still resident in the 126 MB L2
+// -- instead of the ones written first, long evicted by the 1-2 GB that followed (results do not depend on the order)
+int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb, cudaStream_t s, bool reverse) {
   BP_REQUIRE(wl && out.ptr, BP_E_INVALID, "window GEMM: null layer / output");
   if (g_w_sms == 0) {
     int dev = 0;
@@ -1246,6 +1251,7 @@ int wconv_launch(const WLayer* wl, const ActDesc& out, const void* skip, int nb,
   BP_REQUIRE(!skip || (out.b == 1 && !out.f32 && a.N <= 128 && a.ry == 1 && a.rx == 1), BP_E_UNSUPPORTED,
              "window GEMM: residual add on this output layout");
   a.nb = nb;
+  a.reverse = reverse ? 1 : 0;
   a.total_regions = a.nphase * nb * a.nstrips * a.regs_per_strip;
   // per-segment element offsets relative to the row base (see the epilogue)
   {

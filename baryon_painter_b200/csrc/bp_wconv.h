@@ -84,7 +84,7 @@ struct WTiling { int Wt = 0, T_r = 0, gl = 0, nbst = 0; };
 int wconv_build(const WSpec& spec, const ActDesc& in, int nb_max, WLayer** out, int rank = 0, const WTiling* forced = nullptr);
 void wconv_tiling(const WLayer* w, WTiling* t);
 void wconv_free(WLayer* w);
-int wconv_launch(const WLayer* w, const ActDesc& out, const void* skip, int nb, cudaStream_t s);
+int wconv_launch(const WLayer* w, const ActDesc& out, const void* skip, int nb, cudaStream_t s, bool reverse = false);
 int wconv_mma_count(const WLayer* w, int nb, double* cycles_floor);
 
 // lowering (bp_v2.cu)
