@@ -497,6 +497,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
     const int Hs = (OH >> obs) + 1, Ws = (OW >> obs) + 1;
     const long long samp = ob == 1 ? (long long)OH * OW * oC : ((long long)Hs * Ws << (2 * obs)) * oC;
     uint32_t as = 0, apar = 0;
+    const uint32_t acc_cols = (uint32_t)(a.nacc * T_r * N);      // TMEM columns of one accumulator buffer
     for (int reg = blockIdx.x; reg < a.total_regions; reg += gridDim.x) {
       const WRegion R = w_decode(a, reg);
       const WPhase P = a.phase[R.pi];
@@ -550,12 +551,22 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
           tc_fence_after();
           waited = true;
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(a.nacc * T_r * N) + (uint32_t)(mt * N);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + (uint32_t)(mt * N);
         // one 16-column chunk; the loop over a warp's chunks is only unrolled where the residual prefetch needs
         // compile-time indices (sk[k]): the epilogue is instruction-cache sensitive (ncu: no_inst stalls)
         auto chunk = [&](const int k, const int c0) {
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
+          // the chunk's BN shifts come from shared memory: fetched while the TMEM load is in flight (ncu: the packed adds
+          // below stalled on these loads, 19 % of L0's samples)
+          // (residual variants only: 384-thread CTAs have the registers; in the 640-thread variants the extra 8 registers
+          // cost L0 more than the overlap gained)
+          const ulonglong2* shp = reinterpret_cast<const ulonglong2*>(s_shift + c0);
+          ulonglong2 shv[4];
+          if (OUTF32 == 0 && SKIP) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) shv[j] = shp[j];
+          }
           tmem_ld_wait();
           if (SPLIT) {
             // the partial accumulators of the split-precision path, summed to nearest here (the tensor core's own
@@ -608,7 +619,6 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               }
             }
           } else {
-            const ulonglong2* sh2 = reinterpret_cast<const ulonglong2*>(s_shift + c0);   // 4 fp32 = 2 pairs each
             uint4 o[2];
             uint4 ol[2];
             long long offs[2];
@@ -621,7 +631,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ W
               if (ch >= seg_valid || (n0 >> seg_shift) >= P.nseg) continue;   // warp-uniform
               if (!valid) continue;
               if (edge && (y0 + a.seg_oy[seg] >= OH || x0 + a.seg_ox[seg] >= OW)) continue;
-              const ulonglong2 sa = sh2[h * 2], sb = sh2[h * 2 + 1];
+              const ulonglong2 sa = SKIP ? shv[h * 2] : shp[h * 2], sb = SKIP ? shv[h * 2 + 1] : shp[h * 2 + 1];
               unsigned long long x2[4];
               if (SPLIT) {
                 const unsigned long long s1 = w_pack_b64(__float_as_uint(a.acc_scale), __float_as_uint(a.acc_scale));

@@ -432,11 +432,12 @@ def main():
         dom_launches = sum(r[4] for r in dom) or 1
         ach = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
         whole = total_tiles / world * FLOPS_PER_TILE / (ms * 1e-3) / 1e12
-        traffic = None
+        traffic = traffic_step = None
         try:   # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/)
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_per_launch"] if tj.get("tiles_per_launch") == painter.model.net.chunk else None
+            traffic_step = tj.get("whole_step_wconv_dram_bytes")
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": "wconv_kernel: 3x3 128->128 @64x64 residual-block convolution (8 layers)",
@@ -444,7 +445,11 @@ def main():
                 "peak_burst": pk["bf16_tflops_burst"], "frac_burst": ach / pk["bf16_tflops_burst"],
                 "note": "the kernel is timed in one isolated profiled step (clocks near burst): frac_burst is the "
                         "honest fraction for it; whole_net is timed over the long sustained loop: frac (sustained peak)",
-                "traffic": traffic, "peak_source": pk["source"], "launch_ms": dom_ms / dom_launches,
+                "traffic": traffic, "traffic_whole_step": traffic_step,
+                "traffic_note": "DRAM bytes (ncu dram__bytes_read + write) per launch of this kernel, and of all window-GEMM "
+                                "launches of one 256-tile step (24.5 GB = 3.7 ms at the measured copy bandwidth): the 512^2 / "
+                                "256^2 layers are HBM-bound, profiles/r02_summary.md",
+                "peak_source": pk["source"], "launch_ms": dom_ms / dom_launches,
                 "share_of_step": dom_ms / tot,
                 "whole_net": {"achieved": whole, "frac": whole / pk["bf16_tflops"],
                               "frac_burst": whole / pk["bf16_tflops_burst"], "flops_per_tile": FLOPS_PER_TILE}}
