@@ -30,7 +30,7 @@ EXPORTS = ("bp_device_count", "bp_cvae_create", "bp_cgan_create", "bp_net_destro
            "bp_cvae_paint_variance_host", "bp_stitch_accumulate", "bp_stitch_finalize", "bp_zoom_tiles", "bp_zoom_accumulate", "bp_plane_prepare",
            "bp_net_set_debug", "bp_net_read_activation", "bp_net_set_profile", "bp_net_read_profile",
            "bp_net_layer_info", "bp_launch_count", "bp_net_flops_per_tile", "bp_net_chunk",
-           "bp_tuning_set", "bp_tuning_get", "bp_tuning_mode", "bp_rng_normal_host", "bp_cvae_elbo_host",
+           "bp_tuning_set", "bp_tuning_get", "bp_tuning_mode", "bp_rng_normal_host", "bp_cvae_elbo_host", "bp_cvae_paint_host_async", "bp_net_wait",
            "bp_last_error", "bp_version")
 
 # which tensor-core formulation / tiling every layer runs with (see include/baryon_painter_b200.h, "formulation table")
@@ -110,6 +110,8 @@ def load():
     lib.bp_tuning_get.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
     lib.bp_tuning_mode.argtypes = [i32, i32]
     lib.bp_rng_normal_host.argtypes = [i32, u64, u64, vp, ctypes.c_size_t]
+    lib.bp_cvae_paint_host_async.argtypes = [vp, vp, vp, i32, u64, tpp, i32, vp, i32, i32]
+    lib.bp_net_wait.argtypes = [vp, i32]
     lib.bp_cvae_elbo_host.argtypes = [vp, vp, vp, vp, i32, u64, tpp, i32, i32, vp, vp, vp]
     _lib = lib
     # the shipped formulation table: every process builds the same kernels for the same layer, so painted tiles
@@ -236,6 +238,19 @@ class Net:
                                      mode, ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.byref(tp), flags,
                                      out.ctypes.data, n))
         return out
+
+    def cvae_paint_host_async(self, tiles, latent, mode, seed, tparams, flags, out, slot):
+        """Enqueue one batch on I/O slot ``slot`` (see bp_cvae_paint_host_async); returns the objects that must stay
+        alive until ``wait(slot)``."""
+        n = tiles.shape[0]
+        tp, keep = self._tp(*tparams)
+        check(load().bp_cvae_paint_host_async(self.handle, tiles.ctypes.data, None if latent is None else latent.ctypes.data,
+                                              mode, ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.byref(tp), flags,
+                                              out.ctypes.data, n, slot))
+        return (tiles, latent, out, keep)
+
+    def wait(self, slot):
+        check(load().bp_net_wait(self.handle, slot))
 
     def cvae_paint_device(self, tiles_ptr, latent_ptr, mode, seed, tparams, flags, out_ptr, n, stream=0):
         tp, keep = self._tp(*tparams)

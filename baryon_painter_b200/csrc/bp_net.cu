@@ -181,6 +181,8 @@ struct V2Plan {
   int q_cat = -1, q_out = -1;
 };
 
+constexpr int kIoSlots = 3;
+
 struct bp_net {
   int device = 0, kind = NET_CVAE, prec = BP_PREC_F32, max_batch = 0, chunk = 0;
   bool split = false;           // fp32-accurate tensor-core path: split-precision fp16 operands (BP_PREC_F32)
@@ -204,6 +206,14 @@ struct bp_net {
   float likelihood_scaling = 1.f;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr, out_stream = nullptr;
+  // I/O slots of the asynchronous host entry point: batch k + 1 uploads and batch k - 1 downloads while batch k
+  // computes; the caller keeps two batches outstanding, so a third slot is needed for the one being enqueued
+  // (allocated on first use)
+  struct IoSlot {
+    float *d_in = nullptr, *d_out = nullptr, *d_lat = nullptr, *h_lat = nullptr, *h_par = nullptr;
+    cudaEvent_t h2d = nullptr, done = nullptr, out = nullptr;
+    bool used = false;
+  } io[kIoSlots];
   std::vector<cudaEvent_t> ev_ready, ev_chunk_done, ev_out;   // per chunk of the pipelined host path
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int prior_valid = 0;
@@ -259,6 +269,13 @@ static void destroy_net(bp_net* net) {
   for (int i = 0; i < 4; ++i) cudaFree(net->pool[i]);
   cudaFree(net->latent); cudaFree(net->prior_all); cudaFree(net->prior_keep); cudaFree(net->params);
   cudaFree(net->d_in); cudaFree(net->d_out); cudaFree(net->d_lat);
+  for (auto& sl : net->io) {
+    cudaFree(sl.d_in); cudaFree(sl.d_out); cudaFree(sl.d_lat);
+    if (sl.h_lat) cudaFreeHost(sl.h_lat);
+    if (sl.h_par) cudaFreeHost(sl.h_par);
+    for (cudaEvent_t e : {sl.h2d, sl.done, sl.out})
+      if (e) cudaEventDestroy(e);
+  }
   cudaFree(net->var_mean); cudaFree(net->var_m2); cudaFree(net->var_rep);
   cudaFree(net->xq); cudaFree(net->d_x); cudaFree(net->q_cat32); cudaFree(net->q_out32); cudaFree(net->d_sums);
   if (net->h_x) cudaFreeHost(net->h_x);
@@ -965,11 +982,26 @@ static int v2_run(bp_net* net, std::vector<V2Op>& ops, float* final_out, long lo
   return BP_OK;
 }
 
-static int upload_params(bp_net* net, const bp_transform_params* tp, int flags, int n, cudaStream_t s) {
+// `staging`: page-locked [3][max_batch] floats; the per-tile parameters go through it so that the copies are truly
+// asynchronous (a cudaMemcpyAsync from pageable memory first waits for the stream to drain)
+static int upload_params(bp_net* net, const bp_transform_params* tp, int flags, int n, cudaStream_t s, float* staging = nullptr) {
   BP_REQUIRE(tp != nullptr && tp->aux != nullptr, BP_E_INVALID, "transform params / aux plane values missing");
   BP_REQUIRE(!(flags & BP_FLAG_TRANSFORM) || tp->sigma_in, BP_E_INVALID, "sigma_in missing");
   BP_REQUIRE(!(flags & BP_FLAG_INVERSE) || tp->sigma_out, BP_E_INVALID, "sigma_out missing");
   const int mb = net->max_batch;
+  if (staging) {
+    if (tp->sigma_in) {
+      memcpy(staging, tp->sigma_in, sizeof(float) * n);
+      BP_CUDA_TRY(cudaMemcpyAsync(net->params, staging, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    }
+    if (tp->sigma_out) {
+      memcpy(staging + mb, tp->sigma_out, sizeof(float) * n);
+      BP_CUDA_TRY(cudaMemcpyAsync(net->params + mb, staging + mb, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    }
+    memcpy(staging + 2 * mb, tp->aux, sizeof(float) * n);
+    BP_CUDA_TRY(cudaMemcpyAsync(net->params + 2 * mb, staging + 2 * mb, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    return BP_OK;
+  }
   if (tp->sigma_in)
     BP_CUDA_TRY(cudaMemcpyAsync(net->params, tp->sigma_in, sizeof(float) * n, cudaMemcpyHostToDevice, s));
   if (tp->sigma_out)
@@ -1083,7 +1115,7 @@ struct ChunkHooks {
 
 static int cvae_paint_device(bp_net* net, const float* tiles, const float* latent, int mode, uint64_t seed,
                              const bp_transform_params* tp, int flags, float* out, int n, cudaStream_t s,
-                             const ChunkHooks* hooks = nullptr) {
+                             const ChunkHooks* hooks = nullptr, float* param_staging = nullptr) {
   BP_REQUIRE(net && net->kind == NET_CVAE, BP_E_INVALID, "not a CVAE network");
   BP_REQUIRE(n >= 0 && n <= net->max_batch, BP_E_INVALID, "batch %d exceeds max_batch %d", n, net->max_batch);
   BP_REQUIRE(mode == BP_LATENT_GIVEN || mode == BP_LATENT_EPS || mode == BP_LATENT_SEED, BP_E_INVALID,
@@ -1092,7 +1124,7 @@ static int cvae_paint_device(bp_net* net, const float* tiles, const float* laten
   if (n == 0) return BP_OK;
   BP_REQUIRE(tiles && out, BP_E_INVALID, "null tile pointer");
   BP_CUDA_TRY(cudaSetDevice(net->device));
-  int rc = upload_params(net, tp, flags, n, s);
+  int rc = upload_params(net, tp, flags, n, s, param_staging);
   if (rc != BP_OK) return rc;
   const size_t HW = (size_t)net->H * net->W;
   const size_t lhw = (size_t)net->lh * net->lw;
@@ -1528,6 +1560,57 @@ int bp_cgan_paint_host(bp_net* net, const float* tiles, const bp_transform_param
   return paint_host_pipelined(net, tiles, out, n, [&](const ChunkHooks& hooks) {
     return cgan_paint_device(net, net->d_in, tp, flags, net->d_out, n, s, &hooks);
   });
+}
+
+// Asynchronous host entry point for a STREAM of batches: returns once the batch is enqueued; bp_net_wait(net, slot) returns
+// when its result is in `out`.  With the three slots used in turn and two batches kept outstanding, the upload of batch
+// k + 1 and the download of batch k - 1 overlap the kernels of batch k, which run as whole plan chunks (the synchronous entry point has to cut one batch
+// into small pipeline chunks to overlap anything, and pays their launch overheads).  `tiles`, `out` (and `latent`) must stay
+// valid and untouched until the wait; they should be page-locked (pageable buffers make the copies synchronous).
+int bp_cvae_paint_host_async(bp_net* net, const float* tiles, const float* latent, int latent_mode, uint64_t seed,
+                             const bp_transform_params* tp, int flags, float* out, int n, int slot) {
+  BP_REQUIRE(net && net->kind == NET_CVAE, BP_E_INVALID, "not a CVAE network");
+  BP_REQUIRE(slot >= 0 && slot < kIoSlots, BP_E_INVALID, "slot must be 0 .. %d", kIoSlots - 1);
+  BP_REQUIRE(n > 0 && n <= net->max_batch && tiles && out, BP_E_INVALID, "bad batch / null tile pointer");
+  BP_REQUIRE(latent_mode == BP_LATENT_SEED || latent != nullptr, BP_E_INVALID, "latent/eps array missing");
+  BP_CUDA_TRY(cudaSetDevice(net->device));
+  const size_t HW = (size_t)net->H * net->W, lhw = (size_t)net->lh * net->lw;
+  bp_net::IoSlot& io = net->io[slot];
+  if (!io.d_in) {
+    BP_CUDA_TRY(cudaMalloc(&io.d_in, sizeof(float) * HW * net->max_batch));
+    BP_CUDA_TRY(cudaMalloc(&io.d_out, sizeof(float) * HW * net->max_batch));
+    BP_CUDA_TRY(cudaMalloc(&io.d_lat, sizeof(float) * lhw * net->max_batch));
+    BP_CUDA_TRY(cudaMallocHost(&io.h_lat, sizeof(float) * lhw * net->max_batch));
+    BP_CUDA_TRY(cudaMallocHost(&io.h_par, sizeof(float) * 3 * net->max_batch));
+    for (cudaEvent_t* e : {&io.h2d, &io.done, &io.out}) BP_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  cudaStream_t s = net->stream, sin = net->copy_stream, sout = net->out_stream;
+  if (io.used) {
+    BP_CUDA_TRY(cudaEventSynchronize(io.out));             // the slot's previous result has left the device
+    BP_CUDA_TRY(cudaStreamWaitEvent(sin, io.done, 0));     // ... and its inputs are no longer read
+  }
+  if (latent_mode != BP_LATENT_SEED) {
+    memcpy(io.h_lat, latent, sizeof(float) * lhw * n);
+    BP_CUDA_TRY(cudaMemcpyAsync(io.d_lat, io.h_lat, sizeof(float) * lhw * n, cudaMemcpyHostToDevice, sin));
+  }
+  BP_CUDA_TRY(cudaMemcpyAsync(io.d_in, tiles, sizeof(float) * HW * n, cudaMemcpyHostToDevice, sin));
+  BP_CUDA_TRY(cudaEventRecord(io.h2d, sin));
+  BP_CUDA_TRY(cudaStreamWaitEvent(s, io.h2d, 0));
+  int rc = cvae_paint_device(net, io.d_in, io.d_lat, latent_mode, seed, tp, flags, io.d_out, n, s, nullptr, io.h_par);
+  if (rc != BP_OK) return rc;
+  BP_CUDA_TRY(cudaEventRecord(io.done, s));
+  BP_CUDA_TRY(cudaStreamWaitEvent(sout, io.done, 0));
+  BP_CUDA_TRY(cudaMemcpyAsync(out, io.d_out, sizeof(float) * HW * n, cudaMemcpyDeviceToHost, sout));
+  BP_CUDA_TRY(cudaEventRecord(io.out, sout));
+  io.used = true;
+  return BP_OK;
+}
+
+int bp_net_wait(bp_net* net, int slot) {
+  BP_REQUIRE(net && slot >= 0 && slot < kIoSlots, BP_E_INVALID, "bad net / slot");
+  BP_CUDA_TRY(cudaSetDevice(net->device));
+  if (net->io[slot].used) BP_CUDA_TRY(cudaEventSynchronize(net->io[slot].out));
+  return BP_OK;
 }
 
 int bp_cvae_read_prior(bp_net* net, float* z_mu, float* z_log_var, int n) {

@@ -183,6 +183,20 @@ class CVAEModel:
         return torch.from_numpy(mu[:, None]), torch.from_numpy(lv[:, None])
 
 
+class _Ticket:
+    """Handle of an enqueued ``paint_batch_async`` batch."""
+
+    def __init__(self, net, slot, out, keep):
+        self._net, self._slot, self._out, self._keep = net, slot, out, keep
+
+    def wait(self):
+        """block until the batch's painted tiles are in the ``out`` array; returns it"""
+        if self._net is not None:
+            self._net.wait(self._slot)
+            self._net, self._keep = None, None
+        return self._out
+
+
 class CVAEPainter(Painter):
     def __init__(self, filename=None, training_data_set=None, test_data_set=None, architecture="test",
                  compute_device="cuda:0", precision=None, max_batch=16, seed=None):
@@ -290,6 +304,48 @@ class CVAEPainter(Painter):
         if not use_i:
             return out.reshape(n, 1, *out.shape[1:])
         return out
+
+    def paint_batch_async(self, tiles, z=0.0, latents=None, eps=None, seed=None, out=None):
+        """``paint_batch`` for a STREAM of batches: enqueues the batch and returns a ticket; ``ticket.wait()`` returns the
+        painted tiles.  Consecutive calls take three device I/O slots in turn; with two batches kept outstanding the
+        upload of the next batch and the download of the previous one overlap this batch's kernels (which run as whole
+        plan chunks)::
+
+            tickets = []
+            for batch, result in zip(batches, results):                 # page-locked arrays (pinned_empty)
+                tickets.append(painter.paint_batch_async(batch, z=z, eps=eps, out=result))
+                if len(tickets) > 2:
+                    tickets.pop(0).wait()
+            for t in tickets:
+                t.wait()
+
+        ``tiles`` (n <= max_batch) and ``out`` must be page-locked float32 arrays (``baryon_painter_b200.pinned_empty``) and
+        stay untouched until the wait; the fused fiducial transforms are applied."""
+        tiles = np.asarray(tiles)
+        n = tiles.shape[0]
+        if tuple(tiles.shape[1:]) != tuple(self.model.dim_y[1:]) or tiles.dtype != np.float32 or not tiles.flags.c_contiguous:
+            raise ValueError(f"Shape mismatch between input and model: {tiles.shape[1:]} vs {self.model.dim_y} "
+                             "(C-contiguous float32 tiles expected)")
+        if out is None:
+            out = _lib.pinned_empty(tiles.shape)
+        elif out.shape != tiles.shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape %r" % (tiles.shape,))
+        self.model.ensure_batch(n)
+        zs = np.broadcast_to(np.asarray(z, np.float64).reshape(-1), (n,))
+        s_in, s_out, tp = self._sigmas(zs, True, True)
+        lat_shape = (n, *self.model.dim_z[1:])
+        if latents is not None:
+            mode, lat = _lib.BP_LATENT_GIVEN, np.ascontiguousarray(latents, np.float32).reshape(lat_shape)
+        elif eps is not None:
+            mode, lat = _lib.BP_LATENT_EPS, np.ascontiguousarray(eps, np.float32).reshape(lat_shape)
+        else:
+            mode, lat = _lib.BP_LATENT_SEED, None
+        seed = self._next_seed() if seed is None else int(seed)
+        slot = getattr(self, "_slot", 0)
+        self._slot = (slot + 1) % 3
+        keep = self.model.net.cvae_paint_host_async(tiles, lat, mode, seed, (s_in, s_out, zs.astype(np.float32), *tp),
+                                                    _lib.BP_FLAG_TRANSFORM | _lib.BP_FLAG_INVERSE, out, slot)
+        return _Ticket(self.model.net, slot, out, keep)
 
     def paint_batch_device(self, tiles, z=0.0, eps=None, latents=None, seed=None, out=None):
         """Device-resident variant of ``paint_batch`` for callers that keep tiles on the GPU (the lightcone

@@ -143,6 +143,14 @@ int bp_cvae_paint(bp_net* net, const float* tiles, const float* latent, int late
                   void* stream);
 int bp_cvae_paint_host(bp_net* net, const float* tiles, const float* latent, int latent_mode,
                        uint64_t seed, const bp_transform_params* tp, int flags, float* out, int n);
+/* The same for a STREAM of batches (reference: a loop of paint() calls over the tiles of a plane, process_SLICS.py:201-218):
+ * returns once the batch is enqueued on `slot` (0, 1 or 2); bp_net_wait(net, slot) returns when `out` holds the result.
+ * Using the slots in turn and keeping two batches outstanding overlaps the upload of batch k+1 and the download of batch
+ * k-1 with the kernels of batch k.
+ * tiles / latent / out must stay valid until the wait and should be page-locked. */
+int bp_cvae_paint_host_async(bp_net* net, const float* tiles, const float* latent, int latent_mode,
+                             uint64_t seed, const bp_transform_params* tp, int flags, float* out, int n, int slot);
+int bp_net_wait(bp_net* net, int slot);
 /* (z_mu, z_log_var) of the last bp_cvae_paint* call in BP_LATENT_EPS/SEED mode: host [n][h][w] each */
 int bp_cvae_read_prior(bp_net* net, float* z_mu, float* z_log_var, int n);
 /* replaces GAN_Painter.paint (generator forward + transforms) */
