@@ -25,9 +25,22 @@ __device__ __forceinline__ uint16_t f_to16(float v, int fmt) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
-// forward transform; these kernels only feed the 16-bit path, so the fast log (2 ulp) is ample
-__device__ __forceinline__ float f_transform(float x, float inv_sigma, float inv_k, float shift, int on) {
-  return on ? __logf(fmaf(x, inv_sigma, 1.f)) * inv_k - shift : x;
+// forward transform y = ln(x/sigma + 1)/k - shift = lg2(fma(x, 1/sigma, 1)) * (ln 2 / k) - shift.  These kernels only feed
+// the 16-bit path, so the approximate base-2 logarithm (2^-22 absolute) is ample; `ikl2` = ln 2 / k.  The argument is
+// >= 1 for every physical (non-negative) density, so the subnormal handling of __logf is not needed.
+__device__ __forceinline__ float f_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float f_transform(float x, float inv_sigma, float ikl2, float shift, int on) {
+  return on ? fmaf(f_lg2(fmaf(x, inv_sigma, 1.f)), ikl2, -shift) : x;
+}
+constexpr float kLn2 = 0.69314718055994531f, kLog2e = 1.44269504088896341f;
+__device__ __forceinline__ float f_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ float f_act(float v, int act, float p) {
@@ -47,7 +60,7 @@ __global__ void front_prior_kernel(const float* __restrict__ tiles, uint2* __res
                                    const float* __restrict__ aux, float k_in, float shift_in, int do_t, int H, int W, int b,
                                    int fmt) {
   const int n = blockIdx.z;
-  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
+  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = kLn2 / k_in;
   const uint16_t z16 = f_to16(aux[n], fmt);
   const int hw = H * W;
   const int Hs = b > 1 ? H / b + 1 : H, Ws = b > 1 ? W / b + 1 : W;
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(256, 2) front_prior_conv_kernel(const float* _
   const int n = blockIdx.z;
   const int OH = H >> 1, OW = W >> 1;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
+  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = kLn2 / k_in;
   const float z = aux[n];
   const float* src = tiles + (size_t)n * H * W;
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
@@ -174,19 +187,20 @@ __global__ void __launch_bounds__(256, 2) front_prior_conv_kernel(const float* _
     yv[rr][0] = *reinterpret_cast<const unsigned long long*>(&sy[2 * li0 + rr][2 * lj]);
     yv[rr][1] = *reinterpret_cast<const unsigned long long*>(&sy[2 * li0 + rr][2 * lj + 2]);
   }
+  // accumulators start at z * (sum of the in-image z taps) + shift (BN folded)
   unsigned long long acc[4][8];
   {
     const int cc = j == 0 ? 0 : (j == OW - 1 ? 2 : 1);
     float zc[8];
 #pragma unroll
-    for (int co = 0; co < 8; ++co) zc[co] = z * szs[1][cc][co];
+    for (int co = 0; co < 8; ++co) zc[co] = fmaf(z, szs[1][cc][co], fc.shift[co]);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int i = i0 + li0 + p;
       if (i == 0 || i == OH - 1) {                        // warp-uniform
         const int rc = i == 0 ? 0 : 2;
 #pragma unroll
-        for (int co = 0; co < 8; ++co) acc[p][co] = f_pack2(z * szs[rc][cc][co], 0.f);
+        for (int co = 0; co < 8; ++co) acc[p][co] = f_pack2(fmaf(z, szs[rc][cc][co], fc.shift[co]), 0.f);
       } else {
 #pragma unroll
         for (int co = 0; co < 8; ++co) acc[p][co] = f_pack2(zc[co], 0.f);
@@ -208,8 +222,22 @@ __global__ void __launch_bounds__(256, 2) front_prior_conv_kernel(const float* _
 #pragma unroll
         for (int co = 0; co < 8; ++co) acc[p][co] = f_fma2(yv[2 * p + r][qp], w2[co], acc[p][co]);
     }
+  // ReLU / LeakyReLU / PReLU with a slope in [0, 1] are max(a, slope * a); channels >= cout have zero weights, tap
+  // sums and shift, so they come out as 0 without a mask
   const bool lin_act = fc.act == BP_ACT_RELU || fc.act == BP_ACT_LEAKY || fc.act == BP_ACT_PRELU || fc.act == BP_ACT_NONE;
   const float slope = fc.act == BP_ACT_RELU ? 0.f : (fc.act == BP_ACT_NONE ? 1.f : fc.act_param);
+  const bool max_act = lin_act && slope >= 0.f && slope <= 1.f;
+  // store geometry: the x part of the (shifted space-to-depth) address is the same for the four rows
+  const int obs = (ob & (ob - 1)) == 0 ? 31 - __clz(ob) : -1;
+  const int half = ob >> 1, Hs = OH / ob + 1, Ws = OW / ob + 1;
+  size_t xpart, rowpitch;
+  if (ob == 1) {
+    xpart = (size_t)j; rowpitch = (size_t)OW;
+  } else {
+    const int xx = j + half;
+    const int bx = obs >= 0 ? xx >> obs : xx / ob, sx = xx - bx * ob;
+    xpart = (size_t)bx * ob * ob + sx; rowpitch = (size_t)Ws * ob * ob;
+  }
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const int i = i0 + li0 + p;
@@ -217,24 +245,26 @@ __global__ void __launch_bounds__(256, 2) front_prior_conv_kernel(const float* _
     uint32_t pk[4];
 #pragma unroll
     for (int c2 = 0; c2 < 4; ++c2) {
-      float a0 = f_sum2(acc[p][2 * c2]) + fc.shift[2 * c2], a1 = f_sum2(acc[p][2 * c2 + 1]) + fc.shift[2 * c2 + 1];
-      if (lin_act) {                                      // ReLU / LeakyReLU / PReLU: one select
+      float a0 = f_sum2(acc[p][2 * c2]), a1 = f_sum2(acc[p][2 * c2 + 1]);
+      if (max_act) {
+        a0 = fmaxf(a0, a0 * slope);
+        a1 = fmaxf(a1, a1 * slope);
+      } else if (lin_act) {
         a0 = a0 >= 0.f ? a0 : a0 * slope;
         a1 = a1 >= 0.f ? a1 : a1 * slope;
       } else {
-        a0 = f_act(a0, fc.act, fc.act_param);
-        a1 = f_act(a1, fc.act, fc.act_param);
+        a0 = 2 * c2 < fc.cout ? f_act(a0, fc.act, fc.act_param) : 0.f;
+        a1 = 2 * c2 + 1 < fc.cout ? f_act(a1, fc.act, fc.act_param) : 0.f;
       }
-      pk[c2] = f_pack16(2 * c2 < fc.cout ? a0 : 0.f, 2 * c2 + 1 < fc.cout ? a1 : 0.f, fmt);
+      pk[c2] = f_pack16(a0, a1, fmt);
     }
     size_t o;
     if (ob == 1) {
-      o = (((size_t)n * OH + i) * OW + j) * (size_t)oCp;
+      o = (((size_t)n * OH + i) * rowpitch + xpart) * (size_t)oCp;
     } else {
-      const int yy = i + (ob >> 1), xx = j + (ob >> 1);
-      const int by = yy / ob, sy_ = yy - by * ob, bx = xx / ob, sx = xx - bx * ob;
-      const int Hs = OH / ob + 1, Ws = OW / ob + 1;
-      o = (((((size_t)n * Hs + by) * Ws + bx) * ob + sy_) * ob + sx) * (size_t)oCp;
+      const int yy = i + half;
+      const int by = obs >= 0 ? yy >> obs : yy / ob, sy_ = yy - by * ob;
+      o = (((size_t)n * Hs + by) * rowpitch + (size_t)sy_ * ob + xpart) * (size_t)oCp;
     }
     *reinterpret_cast<uint4*>(out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
@@ -255,8 +285,11 @@ int launch_front_prior_conv(const float* tiles, const ActDesc& out, const float*
 
 // ---- decoder input ---------------------------------------------------------------------------------
 // 1 -> 1 channel transposed convolution with k = 2s, p = s/2: two taps per dimension
-__device__ __forceinline__ float up_at(const float* in, int ih, int iw, const float* w, int k, int s, int p, int oy, int ox) {
-  const int r0 = (oy + p) % s, qh = (oy + p) / s, c0 = (ox + p) % s, qw = (ox + p) / s;
+// (`ls` = log2(s) when the stride is a power of two, else -1: the divisions become shifts)
+__device__ __forceinline__ int f_div(int x, int s, int ls) { return ls >= 0 ? x >> ls : x / s; }
+__device__ __forceinline__ float up_at(const float* in, int ih, int iw, const float* w, int k, int s, int ls, int p, int oy,
+                                       int ox) {
+  const int qh = f_div(oy + p, s, ls), r0 = oy + p - qh * s, qw = f_div(ox + p, s, ls), c0 = ox + p - qw * s;
   float acc = 0.f;
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
@@ -289,9 +322,11 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
   // row ranges needed at every level (inclusive), from the band downwards
   int lo[5], hi[5];
   lo[pz.nl] = y0; hi[pz.nl] = min(H, y0 + rows) - 1;
+  int lgs[4];
+  for (int i = 0; i < pz.nl; ++i) lgs[i] = (pz.s[i] & (pz.s[i] - 1)) == 0 ? 31 - __clz(pz.s[i]) : -1;
   for (int i = pz.nl - 1; i >= 0; --i) {
-    lo[i] = max(0, (lo[i + 1] + pz.p[i]) / pz.s[i] - 1);
-    hi[i] = min(lvh[i] - 1, (hi[i + 1] + pz.p[i]) / pz.s[i]);
+    lo[i] = max(0, f_div(lo[i + 1] + pz.p[i], pz.s[i], lgs[i]) - 1);
+    hi[i] = min(lvh[i] - 1, f_div(hi[i + 1] + pz.p[i], pz.s[i], lgs[i]));
   }
   // shared buffers: level i rows [lo[i], hi[i]] x lvw[i]
   float* buf[5];
@@ -304,10 +339,12 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
   __syncthreads();
   for (int l = 0; l + 1 < pz.nl; ++l) {
     const int nr = hi[l + 1] - lo[l + 1] + 1, w1 = lvw[l + 1];
+    const int lw1 = (w1 & (w1 - 1)) == 0 ? 31 - __clz(w1) : -1;
     for (int i = threadIdx.x; i < nr * w1; i += blockDim.x) {
-      const int oy = lo[l + 1] + i / w1, ox = i % w1;
+      const int ry = f_div(i, w1, lw1), oy = lo[l + 1] + ry, ox = i - ry * w1;
       // rows of the source buffer are offset by lo[l]
-      const float v = up_at(buf[l] - (size_t)lo[l] * lvw[l], hi[l] + 1, lvw[l], pz.w[l], pz.k[l], pz.s[l], pz.p[l], oy, ox);
+      const float v = up_at(buf[l] - (size_t)lo[l] * lvw[l], hi[l] + 1, lvw[l], pz.w[l], pz.k[l], pz.s[l], lgs[l], pz.p[l], oy,
+                            ox);
       buf[l + 1][i] = f_act(fmaf(v, pz.scale[l], pz.shift[l]), pz.act[l], pz.act_param[l]);
     }
     __syncthreads();
@@ -315,7 +352,7 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
   const int L = pz.nl - 1;
   const bool fast4 = pz.s[L] == 4 && pz.k[L] == 8 && pz.p[L] == 2 && (W & 3) == 0 && ((W >> 2) & ((W >> 2) - 1)) == 0 &&
                      lvw[L] * 4 == W;
-  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = 1.f / k_in;
+  const float sg = do_t ? 1.f / sigma[n] : 1.f, ik = kLn2 / k_in;
   const uint32_t z16 = f_to16(aux[n], fmt);
   const int nr = hi[pz.nl] - lo[pz.nl] + 1;
   const float* src = buf[L] - (size_t)lo[L] * lvw[L];
@@ -354,7 +391,7 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
       for (int e = 0; e < 4; ++e) {
         float v = fmaf(acc[e], bsc, bsh);
         v = actL == BP_ACT_RELU ? fmaxf(v, 0.f) : f_act(v, actL, ap);
-        lo16[e] = (uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(f_transform(tv[e], sg, ik, shift_in, do_t), fmt) << 16);
+        lo16[e] = f_pack16(v, f_transform(tv[e], sg, ik, shift_in, do_t), fmt);      // one saturating cvt for the pair
       }
       uint4* o = reinterpret_cast<uint4*>(out + p);
       o[0] = make_uint4(lo16[0], z16, lo16[1], z16);
@@ -373,9 +410,9 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
       uint32_t lo16[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float v = up_at(src, hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], pz.p[L], oy, ox + e);
+        float v = up_at(src, hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], lgs[L], pz.p[L], oy, ox + e);
         v = f_act(fmaf(v, pz.scale[L], pz.shift[L]), pz.act[L], pz.act_param[L]);
-        lo16[e] = (uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(f_transform(tv[e], sg, ik, shift_in, do_t), fmt) << 16);
+        lo16[e] = f_pack16(v, f_transform(tv[e], sg, ik, shift_in, do_t), fmt);
       }
       uint4* o = reinterpret_cast<uint4*>(out + p);
       o[0] = make_uint4(lo16[0], z16, lo16[1], z16);
@@ -385,11 +422,11 @@ __global__ void __launch_bounds__(256) front_latent_kernel(const float* __restri
   }
   for (int i = threadIdx.x; i < nr * W; i += blockDim.x) {
     const int oy = y0 + i / W, ox = i % W;
-    float v = up_at(src, hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], pz.p[L], oy, ox);
+    float v = up_at(src, hi[L] + 1, lvw[L], pz.w[L], pz.k[L], pz.s[L], lgs[L], pz.p[L], oy, ox);
     v = f_act(fmaf(v, pz.scale[L], pz.shift[L]), pz.act[L], pz.act_param[L]);
     const size_t p = ((size_t)n * H + oy) * W + ox;
     const float yv = f_transform(tiles[p], sg, ik, shift_in, do_t);
-    out[p] = make_uint2((uint32_t)f_to16(v, fmt) | ((uint32_t)f_to16(yv, fmt) << 16), z16);
+    out[p] = make_uint2(f_pack16(v, yv, fmt), z16);
   }
 }
 
@@ -464,6 +501,8 @@ __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restri
   __syncthreads();
   const int tx = (threadIdx.x % 16) * 4;
   const float sg = tp.post ? post_sigma[n] : 1.f;
+  const bool fast_tail = !tp.precise && tp.act == BP_ACT_SOFTPLUS && tp.post;
+  const float post_a = tp.post_k * kLog2e, post_b = tp.post_shift * tp.post_k * kLog2e;
 #pragma unroll 1
   for (int ty = threadIdx.x / 16; ty < TY; ty += 16) {
     const int y = y0 + ty;
@@ -487,6 +526,17 @@ __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restri
       }
     }
     float o[4];
+    if (fast_tail) {
+      // 16-bit path, Softplus + inverse transform (the shipped networks): base-2 exp / log on the special-function
+      // unit, constants folded -- softplus(v) = ln 2 * lg2(1 + 2^(v log2 e)),
+      // (exp((x + shift) k) - 1) sigma = 2^(x k log2 e + shift k log2 e) * sigma - sigma
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = fmaf(acc[e], tp.scale, tp.shift);
+        const float sp = v > 20.f ? v : kLn2 * f_lg2(1.f + f_ex2(v * kLog2e));
+        o[e] = fmaf(f_ex2(fmaf(sp, post_a, post_b)), sg, -sg);
+      }
+    } else
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float v = fmaf(acc[e], tp.scale, tp.shift);

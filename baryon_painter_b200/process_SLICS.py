@@ -224,11 +224,23 @@ class DeviceBackend:
                                     org.data_ptr(), painted.shape[0], painted.shape[1], falloff, sigma,
                                     self.torch.cuda.current_stream(self.device).cuda_stream)
 
+    @staticmethod
+    def _host_staged(group):
+        """gloo has no device point-to-point / reduce: such a group (CPU-side tests, a box without NCCL) is served
+        through host copies; NCCL groups exchange device memory directly"""
+        import torch.distributed as dist
+        return dist.get_backend(group) == "gloo"
+
     def reduce(self, tensors, dst, group):
         """ONE sum-reduction of a list of same-dtype device tensors to rank ``dst`` (NCCL over NVLink on a GPU box)"""
         import torch.distributed as dist
         flat = self.torch.cat([p.reshape(-1) for p in tensors])
-        dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        if self._host_staged(group):
+            host = flat.cpu()
+            dist.reduce(host, dst=dst, op=dist.ReduceOp.SUM, group=group)
+            flat.copy_(host)
+        else:
+            dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=group)
         out, o = [], 0
         for p in tensors:
             out.append(flat[o:o + p.numel()].reshape(p.shape))
@@ -237,13 +249,15 @@ class DeviceBackend:
 
     def send(self, plane, dst, group):
         import torch.distributed as dist
-        dist.send(plane.contiguous(), dst=dst, group=group)
+        plane = plane.contiguous()
+        dist.send(plane.cpu() if self._host_staged(group) else plane, dst=dst, group=group)
 
     def recv(self, shape, src, group):
         import torch.distributed as dist
-        t = self.torch.empty(shape, dtype=self.torch.float64, device=self.device)
+        staged = self._host_staged(group)
+        t = self.torch.empty(shape, dtype=self.torch.float64, device="cpu" if staged else self.device)
         dist.recv(t, src=src, group=group)
-        return t
+        return t.to(self.device) if staged else t
 
     def finalize_device(self, planes):
         """plane = numerator / denominator (reference :222), staying on the device"""

@@ -168,6 +168,23 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+LIGHTCONE_FIELDS = ("metric", "value", "unit", "n_gpus", "scaling", "ms_per_step", "tiles_per_s", "stages_s_max_over_ranks",
+                    "map_check")
+
+
+class _ZeroEps:
+    """painter wrapper: eps = 0, so that the painted line of sight does not depend on per-rank call counters"""
+
+    def __init__(self, painter):
+        self.p = painter
+        self.compute_device = painter.compute_device
+
+    def paint_batch_device(self, tiles, z=0.0, out=None):
+        import torch
+        eps = torch.zeros((tiles.shape[0], *self.p.model.dim_z[1:]), dtype=torch.float32, device=tiles.device)
+        return self.p.paint_batch_device(tiles, z=z, eps=eps, out=out)
+
+
 def measure_lightcone(args, rank, world, local, precision):
     """BASELINE.json configs[4]: one full synthetic line of sight -- 15 lightcone slices (2 mass planes of 12288^2,
     13 delta planes of 7745^2 pixels, 781 tiles of 512^2) tiled, painted, stitched and projected to a 1549^2 Compton-y
@@ -236,6 +253,7 @@ def measure_lightcone(args, rank, world, local, precision):
     clocks = sampler.stop()
     stages = {}
     ps.paint_lightcone(painter, stage_times=stages, **kw)          # one more pass with per-stage synchronised clocks
+    y_fixed = ps.paint_lightcone(_ZeroEps(painter), **kw)          # latents = prior mean: the same map at every N
     t = torch.tensor([float(np.median(times)), float(np.sum(times))], dtype=torch.float64, device="cuda")
     st = torch.tensor([stages.get(k, 0.0) for k in ("wait_plane", "extract", "paint", "stitch", "project", "reduce")],
                       dtype=torch.float64, device="cuda")
@@ -254,6 +272,9 @@ def measure_lightcone(args, rank, world, local, precision):
         "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"fp16": "f16", "bf16": "bf16"}.get(precision, precision), "data": "synthetic",
         "tiles_per_s": n_tiles / med,
+        "map_check": {"what": "y map painted with eps = 0 (independent of how planes are dealt to ranks): compare "
+                              "across n_gpus", "sum": float(y_fixed.sum()), "l2": float(np.sqrt((y_fixed ** 2).sum())),
+                      "max": float(y_fixed.max())},
         "config": {"workload": "full create_lightcone line of sight (BASELINE.json configs[4]): %d synthetic slices, "
                                "plane pixels x%.2f of SLICS (12288^2 mass / 7745^2 delta), %d tiles of 512^2, quintic "
                                "projection to 1549^2" % (n_z, scale, n_tiles),
@@ -575,7 +596,14 @@ def main():
         if not args.no_lightcone:
             del painter
             lc = measure_lightcone(args, 0, 1, local, args.precision)
-            extra["lightcone"] = {k: lc[k] for k in ("metric", "value", "unit", "ms_per_step", "tiles_per_s", "stages_s_max_over_ranks")}
+            extra["lightcone"] = {k: lc[k] for k in LIGHTCONE_FIELDS}
+    if world > 1 and not args.no_extra and not args.no_lightcone:
+        # configs[4] at N GPUs: ONE line of sight sharded over all ranks (strong scaling; the N = 1 line carries the
+        # single-GPU time, map_check must agree between them)
+        del painter
+        lc = measure_lightcone(args, rank, world, local, args.precision)
+        if rank == 0:
+            extra["lightcone"] = {k: lc[k] for k in LIGHTCONE_FIELDS}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -112,3 +112,74 @@ def test_paint_lightcone_device_equals_two_step():
         y = ps.paint_lightcone(painter, resolution=80, map_size=10.0, cosmo=cosmo, order=5, verbose=False, batch=16,
                                backend=be, **args)
         assert y.shape == (80, 80) and rel_l2(y, ref) <= 1e-9, (trial, rel_l2(y, ref))
+
+
+def _sharded_case(rng_seed=21):
+    import scipy.ndimage
+    rng = np.random.default_rng(rng_seed)
+
+    def field(n):
+        g = scipy.ndimage.gaussian_filter(rng.standard_normal((n, n)), 4.0, mode="wrap")
+        return np.exp(g / g.std() - 0.5).astype(np.float32)
+
+    planes_in = [field(300), field(400), field(400), field(400), field(400)]
+    args = dict(tile_size=100.0, n_pixel_tile=64, LOS=1, z_SLICS=[0.1, 0.2, 0.3, 0.4, 0.5],
+                delta_size=[60.0, 150.0, 150.0, 230.0, 230.0], delta_path=None, massplane_path=None,
+                shifts_path=rng.random((5, 2)), z_slice=[0.11, 0.21, 0.31, 0.41, 0.52])
+    return planes_in, args
+
+
+def _device_rank_main(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import torch.distributed as dist
+    from baryon_painter_b200 import process_SLICS as ps
+    from baryon_painter_b200.painter import CVAEPainter
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    planes_in, args = _sharded_case()
+    args["plane_source"] = lambda i, kind: np.array(planes_in[i])           # a fresh numpy array on every call
+    painter = _FixedEps(CVAEPainter.synthetic(tile_size=64, seed=4, precision="fp16", max_batch=16))
+    be = ps.DeviceBackend("cuda:0")
+    planes = ps.process_SLICS(painter, batch=16, verbose=False, backend=be, rank=rank, world_size=world, **args)
+    y = ps.paint_lightcone(painter, resolution=80, map_size=10.0, cosmo=ps.FlatLCDM(), order=5, verbose=False, batch=16,
+                           backend=be, rank=rank, world_size=world, **args)
+    if rank == 0:
+        q.put(([np.asarray(p) for p in planes], np.asarray(y)))
+    else:
+        assert planes is None and y is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_device_backend_two_ranks():
+    """world_size 2 with the DEVICE backend and numpy planes: whole planes dealt to two ranks (both on
+    cuda:0, gloo group, exchanges staged through the host), a rank that skips planes, the backend re-used across
+    process_SLICS and paint_lightcone.  Equals the single-process run."""
+    import socket
+    import torch.multiprocessing as mp
+    from baryon_painter_b200 import process_SLICS as ps
+    from baryon_painter_b200.painter import CVAEPainter
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_device_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    planes, y = q.get(timeout=900)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    planes_in, args = _sharded_case()
+    args["plane_source"] = lambda i, kind: np.array(planes_in[i])
+    painter = _FixedEps(CVAEPainter.synthetic(tile_size=64, seed=4, precision="fp16", max_batch=16))
+    ref = ps.process_SLICS(painter, batch=16, verbose=False, **args)
+    assert len(planes) == len(ref) == 5
+    for a, b in zip(planes, ref):
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-10, atol=0)
+    y_ref = ps.create_y_map(ref, args["z_SLICS"], 80, 10.0, ps.FlatLCDM(), order=5, verbose=False)
+    assert rel_l2(y, y_ref) <= 1e-9
