@@ -1,6 +1,9 @@
 """Build ``lib/libbaryon_painter_b200.so`` in-tree with nvcc for sm_100a.
 
-    python -m baryon_painter_b200.build [--force] [--verbose]
+    python -m baryon_painter_b200.build [--force] [--verbose] [--developer]
+
+``--developer`` compiles with -DBP_DEVELOPER: the experiment switches read from the environment (``BP_V2_*``,
+``BP_WIN_TIMING`` ...) exist only in such a build; the release library ignores them.
 
 nvcc cross-compiles without a GPU; the shared object travels to the GPU box with the repo
 snapshot (git-ignored, not gpurun-ignored).
@@ -35,9 +38,9 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, developer=False):
     """Compile every .cu (one object per file, in parallel) and link the shared library."""
-    if not force and not _stale():
+    if not force and not developer and not _stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     obj_dir = os.path.join(LIB_DIR, "obj")
@@ -46,7 +49,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DBP_DEVELOPER"] if developer else []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
@@ -67,4 +70,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, developer="--developer" in sys.argv))
