@@ -14,6 +14,6 @@ sel=[r for r in rows[1:] if 75<=int(r[ii])<=99]
 tot=0
 for r in sel:
     v=float(r[vi].replace(',','')); tot+=v
-    print(r[ii], r[ki][:50], v)
+    print(r[ii], r[ki][:62], v)
 print('sum', tot)
 PY
