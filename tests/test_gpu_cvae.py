@@ -411,3 +411,27 @@ def test_async_stream_matches_sync_calls():
     assert np.array_equal(a, p.paint_batch(batches[0], z=0.0, seed=7))
     with pytest.raises(ValueError, match="Shape mismatch"):
         p.paint_batch_async(np.zeros((2, 32, 32), np.float32))
+
+
+@pytest.mark.parametrize("tile,precision", [(96, "fp16"), (96, "fp32"), (160, "fp16"), (256, "fp16")])
+def test_other_tile_sizes_vs_oracle(tile, precision):
+    """tile sizes other than the fixtures' powers of two (the reference network is fully convolutional: any multiple of
+    32): widths that are not powers of two take the general index arithmetic of the front kernels, partial M-tiles
+    and layer shapes without an entry in the formulation table; ragged batch of 3."""
+    import torch
+    from oracle.cvae_oracle import CVAEOracle
+    from baryon_painter_b200 import arch, synthetic, transforms
+    torch.set_num_threads(os.cpu_count())
+    A = arch.fiducial_cvae_architecture(tile)
+    sd = synthetic.synthetic_cvae_state_dict(A, seed=21)
+    stats = transforms.fiducial_stats()
+    orc = CVAEOracle(A, sd)
+    p = _painter(tile, 21, precision, max_batch=2)
+    tiles = synthetic.synthetic_dm_tiles(3, tile, seed0=900)
+    zs = np.array([0.0, 0.4, 1.2])
+    eps = synthetic.synthetic_latents(3, (tile // 32, tile // 32), seed=5)
+    ref = orc.paint_batch(tiles, zs, stats, eps=eps)
+    out = p.paint_batch(tiles, z=zs, eps=eps)
+    assert out.shape == (3, tile, tile)
+    for i in range(3):
+        assert rel_l2(out[i], ref[i]) <= TOL[precision], (i, rel_l2(out[i], ref[i]))
