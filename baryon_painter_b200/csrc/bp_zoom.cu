@@ -36,12 +36,22 @@ __global__ void zoom_crop_kernel(const T* __restrict__ plane, int ph, int pw, co
   const int y = blockIdx.y;
   int yy = (r0 + y) % ph;
   if (yy < 0) yy += ph;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < side; x += gridDim.x * blockDim.x) {
+  // four elements per thread, a block's width apart: the four loads are in flight together (one element per thread
+  // left the kernel latency bound at a few hundred GB/s)
+  const int xb = blockIdx.x * (4 * blockDim.x) + threadIdx.x;
+  double v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = xb + k * blockDim.x;
     int xx = (c0 + x) % pw;
     if (xx < 0) xx += pw;
-    const double v = (double)plane[(size_t)yy * pw + xx];
+    v[k] = x < side ? (double)plane[(size_t)yy * pw + xx] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = xb + k * blockDim.x;
     // float64 planes are the painted planes on their way into the y-map: NaN -> 0 as create_y_map does (:54)
-    work[((size_t)n * side + y) * side + x] = (sizeof(T) == 8 && v != v) ? 0.0 : v;
+    if (x < side) work[((size_t)n * side + y) * side + x] = (sizeof(T) == 8 && v[k] != v[k]) ? 0.0 : v[k];
   }
 }
 
@@ -118,7 +128,15 @@ __device__ __forceinline__ double zoom_causal_enter(const double* in, size_t st,
     return *first;
   }
   double prev = 0.0;
-  for (int i = i0 - H; i < i0; ++i) prev = g * in[i * st] + z * prev;
+  int i = i0 - H;
+  for (; i + 8 <= i0; i += 8) {       // the loads do not depend on the recursion: eight in flight per thread
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = in[(size_t)(i + k) * st];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) prev = g * x[k] + z * prev;
+  }
+  for (; i < i0; ++i) prev = g * in[i * st] + z * prev;
   return prev;
 }
 
@@ -135,7 +153,18 @@ __global__ void zoom_cols_causal_kernel(const double* __restrict__ in, double* _
   double first;
   double prev = zoom_causal_enter(in + off, st, i0, z, g, H, mirror, &wrote0, &first);
   if (wrote0) out[off] = first;
-  for (int i = wrote0 ? 1 : i0; i < i1; ++i) {
+  int i = wrote0 ? 1 : i0;
+  for (; i + 8 <= i1; i += 8) {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = in[off + (size_t)(i + k) * st];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      prev = g * x[k] + z * prev;
+      out[off + (size_t)(i + k) * st] = prev;
+    }
+  }
+  for (; i < i1; ++i) {
     prev = g * in[off + i * st] + z * prev;
     out[off + i * st] = prev;
   }
@@ -160,7 +189,24 @@ __global__ void zoom_cols_anticausal_kernel(const double* __restrict__ in, doubl
     next = 0.0;
     i = i1 + H - 1;
   }
+  for (; i - 7 >= i1; i -= 8) {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = in[off + (size_t)(i - k) * st];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) next = z * (next - x[k]);
+  }
   for (; i >= i1; --i) next = z * (next - in[off + i * st]);
+  for (; i - 7 >= i0; i -= 8) {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = in[off + (size_t)(i - k) * st];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      next = z * (next - x[k]);
+      out[off + (size_t)(i - k) * st] = next;
+    }
+  }
   for (; i >= i0; --i) {
     next = z * (next - in[off + i * st]);
     out[off + i * st] = next;
@@ -185,7 +231,15 @@ __global__ void __launch_bounds__(32 * kRowWarps) zoom_rows_kernel(const double*
   const int H = zoom_horizon(z), i0 = j * kSeg, i1 = min(side, i0 + kSeg);
   auto load = [&](int c0) {           // columns c0 .. c0 + 31 of the 32 rows
     __syncwarp();
-    for (int r = 0; r < nrows; ++r) tile[r][lane] = (c0 + lane >= 0 && c0 + lane < side) ? in[base + (size_t)r * side + c0 + lane] : 0.0;
+    const bool cin = c0 + lane >= 0 && c0 + lane < side;
+#pragma unroll
+    for (int r8 = 0; r8 < 32; r8 += 8) {            // eight row loads in flight, then their shared-memory stores
+      double x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = (cin && r8 + k < nrows) ? in[base + (size_t)(r8 + k) * side + c0 + lane] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tile[r8 + k][lane] = x[k];
+    }
     __syncwarp();
   };
   auto store = [&](int c0, int lo, int hi) {   // columns [lo, hi) of the chunk at c0
@@ -442,7 +496,7 @@ extern "C" int bp_zoom_tiles(int device, const float* plane, int plane_h, int pl
   double* work = zoom_workspace(device, 2 * (size_t)n * side * side);
   BP_REQUIRE(work, BP_E_NOMEM, "zoom_tiles: %zu bytes of workspace", 2 * (size_t)n * side * side * sizeof(double));
   const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
-  zoom_crop_kernel<float><<<dim3((side + 255) / 256, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
+  zoom_crop_kernel<float><<<dim3((side + 1023) / 1024, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
   int rc = zoom_prefilter(work, work + (size_t)n * side * side, side, n, 3, mirror, s);
   if (rc != BP_OK) return rc;
   zoom_eval_kernel<3, false><<<dim3((out_side + 127) / 128, out_side, n), 128, 0, s>>>(work, side, out_side, mirror, out, 1.0);
@@ -462,7 +516,7 @@ extern "C" int bp_zoom_accumulate(int device, const double* plane, int side, int
   double* work = zoom_workspace(device, 2 * (size_t)side * side);
   BP_REQUIRE(work, BP_E_NOMEM, "zoom_accumulate: %zu bytes of workspace", 2 * (size_t)side * side * sizeof(double));
   const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
-  zoom_crop_kernel<double><<<dim3((side + 255) / 256, side, 1), 256, 0, s>>>(plane, side, side, nullptr, side, work);
+  zoom_crop_kernel<double><<<dim3((side + 1023) / 1024, side, 1), 256, 0, s>>>(plane, side, side, nullptr, side, work);
   int rc = zoom_prefilter(work, work + (size_t)side * side, side, 1, order, mirror, s);
   if (rc != BP_OK) return rc;
   const dim3 grid((out_side + 127) / 128, out_side, 1);
