@@ -107,211 +107,163 @@ __global__ void zoom_filter_kernel(double* __restrict__ work, int side, int ntil
 // samples (32 for the cubic pole, 50 / 14 for the quintic ones).  So (1) the boundary sums of scipy's initialisation
 // stop after `horizon` terms and z^(len-1) vanishes from them -- same float64 result to the last bits; (2) a line is
 // cut into segments of kSeg samples, each warmed up from a zero state over the `horizon` samples in front of it
-// (behind it for the anticausal sweep): every (line, segment) pair is an independent thread, which fills the
-// machine even for the four 7000^2 crops of a near lightcone plane.  Sweeps are out of place (in -> out), because a
-// segment's warm-up reads what its neighbour is about to overwrite.
+// (behind it for the anticausal sweep): (32 lines, segment) blocks are independent, which fills the machine even for
+// the four 7000^2 crops of a near lightcone plane.  Sweeps are out of place (in -> out), because a segment's warm-up
+// reads what its neighbour is about to overwrite.
 constexpr int kSeg = 256;
 __device__ __forceinline__ int zoom_horizon(double z) { return (int)ceil(-41.4465 / log(fabs(z))); }
 
-// value of sample i0 - 1 of the causal recursion (state entering segment [i0, ...)), reading `in` with stride st
-__device__ __forceinline__ double zoom_causal_enter(const double* in, size_t st, int i0, double z, double g, int H, int mirror,
-                                                    bool* wrote0, double* first) {
-  *wrote0 = false;
-  if (i0 == 0) {
-    double z_i = 1.0, s = 0.0;
-    for (int i = 0; i < H; ++i) {
-      s += z_i * (g * in[i * st]);
-      z_i *= z;
-    }
-    *first = mirror ? s : s * z + g * in[0];
-    *wrote0 = true;
-    return *first;
-  }
-  double prev = 0.0;
-  int i = i0 - H;
-  for (; i + 8 <= i0; i += 8) {       // the loads do not depend on the recursion: eight in flight per thread
-    double x[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = in[(size_t)(i + k) * st];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) prev = g * x[k] + z * prev;
-  }
-  for (; i < i0; ++i) prev = g * in[i * st] + z * prev;
-  return prev;
+// ---- both recursions of a direction in ONE pass over shared memory ------------------------------------------
+// Block = 32 lines x one segment [i0, i1) plus a halo of Hh = sum of the poles' horizons on either side (clipped at
+// the line ends).  The block loads the window, warp 0 runs, per pole, the causal and then the anticausal recursion of
+// its 32 lines over the whole window in shared memory (exact scipy start / end conditions where the window touches a
+// line end, a zero state elsewhere: what the halo is for) and the block writes the segment.  One read of 1.25-1.5x
+// the data and one write per direction instead of two reads and two writes: the sweeps are bandwidth bound (the crops
+// of a line of sight are 21 GB per float64 pass).  Two blocks per SM: one loads / stores while the other recurses.
+constexpr int kSweepThreads = 256;
+constexpr int kSweepSeg = 128;      // 32 lines x (128 + 2 x 32) float64 = 48 KB: four blocks per SM, four recursing warps
+__device__ __forceinline__ void zoom_cp8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
 }
-
-// columns: thread = (column, segment); neighbouring threads read neighbouring addresses
-__global__ void zoom_cols_causal_kernel(const double* __restrict__ in, double* __restrict__ out, int side, int ntiles, int mirror,
-                                        double z, double g) {
-  const int nseg = (side + kSeg - 1) / kSeg;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)ntiles * nseg * side) return;
-  const int l = (int)(t % side), j = (int)((t / side) % nseg), n = (int)(t / ((long long)side * nseg));
-  const size_t st = (size_t)side, off = (size_t)n * side * side + l;
-  const int H = zoom_horizon(z), i0 = j * kSeg, i1 = min(side, i0 + kSeg);
-  bool wrote0;
-  double first;
-  double prev = zoom_causal_enter(in + off, st, i0, z, g, H, mirror, &wrote0, &first);
-  if (wrote0) out[off] = first;
-  int i = wrote0 ? 1 : i0;
-  for (; i + 8 <= i1; i += 8) {
-    double x[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = in[off + (size_t)(i + k) * st];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      prev = g * x[k] + z * prev;
-      out[off + (size_t)(i + k) * st] = prev;
-    }
-  }
-  for (; i < i1; ++i) {
-    prev = g * in[off + i * st] + z * prev;
-    out[off + i * st] = prev;
-  }
-}
-// in = causal output.  The last sample starts from scipy's exact end condition; other segments warm up from zero
-__global__ void zoom_cols_anticausal_kernel(const double* __restrict__ in, double* __restrict__ out, int side, int ntiles,
-                                            int mirror, double z) {
-  const int nseg = (side + kSeg - 1) / kSeg;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)ntiles * nseg * side) return;
-  const int l = (int)(t % side), j = (int)((t / side) % nseg), n = (int)(t / ((long long)side * nseg));
-  const size_t st = (size_t)side, off = (size_t)n * side * side + l;
-  const int H = zoom_horizon(z), i0 = j * kSeg, i1 = min(side, i0 + kSeg);
-  double next;
-  int i;
-  if (i1 + H >= side - 1) {            // close enough to the end: start from the exact end condition
-    const double a = in[off + (size_t)(side - 2) * st], b = in[off + (size_t)(side - 1) * st];
-    next = mirror ? (z * a + b) * z / (z * z - 1.0) : b * (z / (z - 1.0));
-    if (i1 == side) out[off + (size_t)(side - 1) * st] = next;
-    i = side - 2;
-  } else {
-    next = 0.0;
-    i = i1 + H - 1;
-  }
-  for (; i - 7 >= i1; i -= 8) {
-    double x[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = in[off + (size_t)(i - k) * st];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) next = z * (next - x[k]);
-  }
-  for (; i >= i1; --i) next = z * (next - in[off + i * st]);
-  for (; i - 7 >= i0; i -= 8) {
-    double x[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = in[off + (size_t)(i - k) * st];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      next = z * (next - x[k]);
-      out[off + (size_t)(i - k) * st] = next;
-    }
-  }
-  for (; i >= i0; --i) {
-    next = z * (next - in[off + i * st]);
-    out[off + i * st] = next;
-  }
-}
-
-// rows: warp = (32 rows, segment); 32 x 32 chunks go through shared memory so that global accesses stay coalesced
-// (lane = column while loading / storing, lane = row while recursing)
-constexpr int kRowWarps = 4;
-template <bool CAUSAL>
-__global__ void __launch_bounds__(32 * kRowWarps) zoom_rows_kernel(const double* __restrict__ in, double* __restrict__ out, int side,
-                                                                  int ntiles, int mirror, double z, double g) {
-  __shared__ double sm[kRowWarps][32][33];
+// CROP (row sweep only): the window is read straight from the float32 plane with the periodic wrap of get_tile
+// (`origins[n]` = top-left pixel of crop n) instead of from a float64 crop buffer: no separate crop pass
+struct ZoomCrop {
+  const float* plane;
+  const int* origins;
+  int ph, pw;
+};
+template <bool ROWS, bool CROP>
+__global__ void __launch_bounds__(kSweepThreads) zoom_sweep_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                                   int side, int ntiles, int mirror, int npoles, double z0,
+                                                                   double z1, double gain, int Hh, ZoomCrop cr) {
+  extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rblocks = (side + 31) / 32, nseg = (side + kSeg - 1) / kSeg;
-  const long long wid = (long long)blockIdx.x * kRowWarps + warp;
-  if (wid >= (long long)ntiles * rblocks * nseg) return;
-  const int j = (int)(wid % nseg), rb = (int)((wid / nseg) % rblocks), n = (int)(wid / ((long long)nseg * rblocks));
-  const int r0 = rb * 32, nrows = min(32, side - r0);
-  const size_t base = (size_t)n * side * side + (size_t)r0 * side;
-  double (*tile)[33] = sm[warp];
-  const int H = zoom_horizon(z), i0 = j * kSeg, i1 = min(side, i0 + kSeg);
-  auto load = [&](int c0) {           // columns c0 .. c0 + 31 of the 32 rows
-    __syncwarp();
-    const bool cin = c0 + lane >= 0 && c0 + lane < side;
+  constexpr int NW = kSweepThreads / 32;
+  const int nseg = (side + kSweepSeg - 1) / kSweepSeg, lblocks = (side + 31) / 32;
+  const long long bid = blockIdx.x;
+  const int j = (int)(bid % nseg), lb = (int)((bid / nseg) % lblocks), n = (int)(bid / ((long long)nseg * lblocks));
+  const int l0 = lb * 32, nl = min(32, side - l0);
+  const int i0 = j * kSweepSeg, i1 = min(side, i0 + kSweepSeg);
+  const int a = max(0, i0 - Hh), b = min(side, i1 + Hh), len = b - a;
+  const int pitch = len | 1;                       // ROWS: sm[line][i], odd pitch; columns: sm[i][line]
+  const size_t base = (size_t)n * side * side;
+  // ---- load: asynchronous 8-byte copies, the whole window of the block in flight at once (register-staged loads
+  // left 8 KB in flight per block and the load phase latency bound)
+  if (ROWS && CROP) {
+    const int r0 = cr.origins[2 * n], c0 = cr.origins[2 * n + 1];
+    int x0 = (c0 + a + lane) % cr.pw;
+    if (x0 < 0) x0 += cr.pw;
+    for (int line = warp; line < nl; line += NW) {
+      int yy = (r0 + l0 + line) % cr.ph;
+      if (yy < 0) yy += cr.ph;
+      const float* src = cr.plane + (size_t)yy * cr.pw;
+      double* dst = sm + line * pitch;
+      int xx = x0;
+      for (int i = lane; i < len; i += 256) {          // eight loads in flight, then their conversions
+        float x[8];
+        int xk = xx;
 #pragma unroll
-    for (int r8 = 0; r8 < 32; r8 += 8) {            // eight row loads in flight, then their shared-memory stores
-      double x[8];
+        for (int k = 0; k < 8; ++k) {
+          x[k] = i + 32 * k < len ? src[xk] : 0.f;
+          xk += 32;
+          if (xk >= cr.pw) xk -= cr.pw;
+        }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = (cin && r8 + k < nrows) ? in[base + (size_t)(r8 + k) * side + c0 + lane] : 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tile[r8 + k][lane] = x[k];
+        for (int k = 0; k < 8; ++k)
+          if (i + 32 * k < len) dst[i + 32 * k] = (double)x[k];
+        xx = xk;
+      }
     }
-    __syncwarp();
-  };
-  auto store = [&](int c0, int lo, int hi) {   // columns [lo, hi) of the chunk at c0
-    __syncwarp();
-    for (int r = 0; r < nrows; ++r)
-      if (c0 + lane >= lo && c0 + lane < hi) out[base + (size_t)r * side + c0 + lane] = tile[r][lane];
-    __syncwarp();
-  };
-  if (CAUSAL) {
-    double prev = 0.0;
-    int c_begin;                      // first chunk whose samples are written
-    if (i0 == 0) {
-      double z_i = 1.0, s = 0.0;
-      for (int c0 = 0; c0 < H; c0 += 32) {
-        load(c0);
-        for (int k = 0; k < 32 && c0 + k < H; ++k) {
-          s += z_i * (g * tile[lane][k]);
+  } else if (ROWS) {
+    for (int line = warp; line < nl; line += NW) {
+      const double* src = in + base + (size_t)(l0 + line) * side + a;
+      double* dst = sm + line * pitch;
+      for (int i = lane; i < len; i += 32) zoom_cp8(dst + i, src + i);
+    }
+  } else {
+    const double* src = in + base + (size_t)a * side + l0 + lane;
+    if (lane < nl)
+      for (int i = warp; i < len; i += NW) zoom_cp8(sm + i * 32 + lane, src + (size_t)i * side);
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- recursions: thread = line
+  if (warp == 0 && lane < nl) {
+    double* c = ROWS ? sm + lane * pitch : sm + lane;
+    const int st = ROWS ? 1 : 32;
+#define S(i) c[(i) * st]
+    for (int p = 0; p < npoles; ++p) {
+      const double z = p == 0 ? z0 : z1, g = p == 0 ? gain : 1.0;
+      const int H = zoom_horizon(z);
+      double prev;
+      int i;
+      if (a == 0) {
+        double z_i = 1.0, sum = 0.0;
+        for (int k = 0; k < H && k < len; ++k) {
+          sum += z_i * (g * S(k));
           z_i *= z;
         }
+        prev = mirror ? sum : sum * z + g * S(0);
+        S(0) = prev;
+        i = 1;
+      } else {
+        prev = 0.0;
+        i = 0;
       }
-      prev = s;                       // becomes sample 0 below (mirror: s; reflect: s z + g c[0])
-      c_begin = 0;
-    } else {
-      const int w0 = ((i0 - H) / 32) * 32;       // warm-up over [i0 - H, i0)
-      for (int c0 = w0; c0 < i0; c0 += 32) {
-        load(c0);
-        for (int k = 0; k < 32; ++k)
-          if (c0 + k >= i0 - H && c0 + k < i0) prev = g * tile[lane][k] + z * prev;
+      for (; i + 8 <= len; i += 8) {
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = S(i + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          prev = g * x[k] + z * prev;
+          S(i + k) = prev;
+        }
       }
-      c_begin = i0;
+      for (; i < len; ++i) {
+        prev = g * S(i) + z * prev;
+        S(i) = prev;
+      }
+      double next;
+      if (b == side) {
+        const double ca = S(len - 2), cb = S(len - 1);
+        next = mirror ? (z * ca + cb) * z / (z * z - 1.0) : cb * (z / (z - 1.0));
+        S(len - 1) = next;
+        i = len - 2;
+      } else {
+        next = 0.0;
+        i = len - 1;
+      }
+      for (; i - 7 >= 0; i -= 8) {
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = S(i - k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          next = z * (next - x[k]);
+          S(i - k) = next;
+        }
+      }
+      for (; i >= 0; --i) {
+        next = z * (next - S(i));
+        S(i) = next;
+      }
     }
-    for (int c0 = c_begin; c0 < i1; c0 += 32) {
-      load(c0);
-      for (int k = 0; k < 32 && c0 + k < i1; ++k) {
-        if (c0 + k == 0) prev = mirror ? prev : prev * z + g * tile[lane][0];
-        else prev = g * tile[lane][k] + z * prev;
-        tile[lane][k] = prev;
-      }
-      store(c0, i0, i1);
+#undef S
+  }
+  __syncthreads();
+  // ---- store the segment
+  const int o0 = i0 - a, no = i1 - i0;
+  if (ROWS) {
+    for (int line = warp; line < nl; line += NW) {
+      double* dst = out + base + (size_t)(l0 + line) * side + i0;
+      const double* src = sm + line * pitch + o0;
+      for (int i = lane; i < no; i += 32) dst[i] = src[i];
     }
-  } else {
-    double next = 0.0;
-    int i;                            // next sample to process (descending)
-    if (i1 + H >= side - 1) {
-      // exact end condition from the causal output's last two samples
-      const int cl = ((side - 1) / 32) * 32;
-      load(cl);
-      const double b = tile[lane][side - 1 - cl];
-      double a;
-      if (side - 2 >= cl) a = tile[lane][side - 2 - cl];
-      else { load(cl - 32); a = tile[lane][31]; }
-      next = mirror ? (z * a + b) * z / (z * z - 1.0) : b * (z / (z - 1.0));
-      i = side - 2;
-      if (i1 == side) {               // this segment owns the last sample
-        load(cl);
-        tile[lane][side - 1 - cl] = next;
-        store(cl, side - 1, side);
-      }
-    } else {
-      i = i1 + H - 1;
-    }
-    const double end_val = next;      // (only meaningful on the exact-end branch)
-    for (int c0 = (i / 32) * 32; c0 + 31 >= i0 && i >= i0; c0 -= 32) {
-      load(c0);
-      if (i1 == side && c0 <= side - 1 && side - 1 < c0 + 32) tile[lane][side - 1 - c0] = end_val;   // keep the last sample
-      for (int k = min(31, i - c0); k >= 0 && c0 + k >= i0; --k) {
-        next = z * (next - tile[lane][k]);
-        tile[lane][k] = next;
-        i = c0 + k - 1;
-      }
-      store(c0, i0, i1);
-    }
+  } else if (lane < nl) {
+    double* dst = out + base + (size_t)i0 * side + l0 + lane;
+    for (int i = warp; i < no; i += NW) dst[(size_t)i * side] = sm[(o0 + i) * 32 + lane];
   }
 }
 
@@ -448,7 +400,10 @@ constexpr double kPole5a = -0.43057534709997381;       // sqrt(67.5 - sqrt(4436.
 constexpr double kPole5b = -0.043096288203264652;      // sqrt(67.5 + sqrt(4436.25)) - sqrt(26.25) - 6.5
 
 // prefilter (rows, then columns) of n cropped tiles already in `work`; `tmp` is a second buffer of the same size
-int zoom_prefilter(double* work, double* tmp, int side, int n, int order, int mirror, cudaStream_t s) {
+// `crop`: read the tiles straight from a float32 plane (long lines only; the caller skips its crop pass)
+bool zoom_fuses_crop(int side) { return side > 2 * kSeg; }
+int zoom_prefilter(double* work, double* tmp, int side, int n, int order, int mirror, cudaStream_t s,
+                   const ZoomCrop* crop = nullptr) {
   const long long lines = (long long)n * side;
   const int fb = 64;
   const int npoles = order == 3 ? 1 : 2;
@@ -460,20 +415,27 @@ int zoom_prefilter(double* work, double* tmp, int side, int n, int order, int mi
       const double z = p == 0 ? p0 : p1;
       gain *= (1.0 - z) * (1.0 - 1.0 / z);
     }
-    const int nseg = (side + kSeg - 1) / kSeg;
-    const long long rwarps = (long long)n * ((side + 31) / 32) * nseg, cthreads = lines * nseg;
-    const unsigned rgrid = (unsigned)((rwarps + kRowWarps - 1) / kRowWarps), cgrid = (unsigned)((cthreads + 127) / 128);
-    for (int p = 0; p < npoles; ++p) {
-      const double z = p == 0 ? p0 : p1;
-      zoom_rows_kernel<true><<<rgrid, 32 * kRowWarps, 0, s>>>(work, tmp, side, n, mirror, z, p == 0 ? gain : 1.0);
-      zoom_rows_kernel<false><<<rgrid, 32 * kRowWarps, 0, s>>>(tmp, work, side, n, mirror, z, 1.0);
+    // sum of the poles' horizons (host copy of zoom_horizon)
+    int Hh = 0;
+    for (int p = 0; p < npoles; ++p) Hh += (int)ceil(-41.4465 / log(fabs(p == 0 ? p0 : p1)));
+    const int nseg = (side + kSweepSeg - 1) / kSweepSeg;
+    const long long blocks = (long long)n * ((side + 31) / 32) * nseg;
+    const size_t smem = sizeof(double) * 32 * (size_t)((kSweepSeg + 2 * Hh) | 1);
+    static bool attr = false;
+    if (!attr) {
+      BP_CUDA_TRY(cudaFuncSetAttribute(zoom_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      BP_CUDA_TRY(cudaFuncSetAttribute(zoom_sweep_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      BP_CUDA_TRY(cudaFuncSetAttribute(zoom_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      attr = true;
     }
-    for (int p = 0; p < npoles; ++p) {
-      const double z = p == 0 ? p0 : p1;
-      zoom_cols_causal_kernel<<<cgrid, 128, 0, s>>>(work, tmp, side, n, mirror, z, p == 0 ? gain : 1.0);
-      zoom_cols_anticausal_kernel<<<cgrid, 128, 0, s>>>(tmp, work, side, n, mirror, z);
-    }
-    launch_counter() += 4 * npoles;
+    BP_REQUIRE(smem <= 112 * 1024 && blocks < (1ll << 31), BP_E_UNSUPPORTED, "zoom prefilter: window of %zu bytes", smem);
+    const ZoomCrop none{nullptr, nullptr, 0, 0};
+    if (crop)
+      zoom_sweep_kernel<true, true><<<(unsigned)blocks, kSweepThreads, smem, s>>>(nullptr, tmp, side, n, mirror, npoles, p0, p1, gain, Hh, *crop);
+    else
+      zoom_sweep_kernel<true, false><<<(unsigned)blocks, kSweepThreads, smem, s>>>(work, tmp, side, n, mirror, npoles, p0, p1, gain, Hh, none);
+    zoom_sweep_kernel<false, false><<<(unsigned)blocks, kSweepThreads, smem, s>>>(tmp, work, side, n, mirror, npoles, p0, p1, gain, Hh, none);
+    launch_counter() += 2;
   } else {
     zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, (long long)side, 1LL, mirror, npoles, p0, p1);
     zoom_filter_kernel<<<(unsigned)((lines + fb - 1) / fb), fb, 0, s>>>(work, side, n, 1LL, (long long)side, mirror, npoles, p0, p1);
@@ -496,8 +458,10 @@ extern "C" int bp_zoom_tiles(int device, const float* plane, int plane_h, int pl
   double* work = zoom_workspace(device, 2 * (size_t)n * side * side);
   BP_REQUIRE(work, BP_E_NOMEM, "zoom_tiles: %zu bytes of workspace", 2 * (size_t)n * side * side * sizeof(double));
   const int mirror = mode == BP_ZOOM_MIRROR ? 1 : 0;
-  zoom_crop_kernel<float><<<dim3((side + 1023) / 1024, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
-  int rc = zoom_prefilter(work, work + (size_t)n * side * side, side, n, 3, mirror, s);
+  const ZoomCrop crop{plane, origins, plane_h, plane_w};
+  const bool fused = zoom_fuses_crop(side);
+  if (!fused) zoom_crop_kernel<float><<<dim3((side + 1023) / 1024, side, n), 256, 0, s>>>(plane, plane_h, plane_w, origins, side, work);
+  int rc = zoom_prefilter(work, work + (size_t)n * side * side, side, n, 3, mirror, s, fused ? &crop : nullptr);
   if (rc != BP_OK) return rc;
   zoom_eval_kernel<3, false><<<dim3((out_side + 127) / 128, out_side, n), 128, 0, s>>>(work, side, out_side, mirror, out, 1.0);
   launch_counter() += 2;

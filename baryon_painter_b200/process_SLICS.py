@@ -361,9 +361,9 @@ def _plane_geometry(delta_size_i, tile_size, n_pixel_tile):
 
 def plane_cost(kind, tiles_per_side, delta_size_i, tile_size):
     """Device seconds one slice costs its owner, for ``plan_planes``: painting is per tile (36 us on a B200); the tile
-    extraction runs the cubic-spline prefilter over every source pixel of every (overlapping) crop, 2.6e-11 s per crop
-    pixel (measured: 65 ms of a 131 ms line of sight, bench.py --config lightcone), which is nearly the same for
-    every delta plane however many tiles it is cut into; plus the upload of the plane itself."""
+    extraction runs the cubic-spline prefilter over every source pixel of every (overlapping) crop, 1.6e-11 s per crop
+    pixel (measured: 43 ms of an 88 ms line of sight with 2.7 G crop pixels, bench.py --config lightcone), which is
+    nearly the same for every delta plane however many tiles it is cut into; plus the upload of the plane itself."""
     n = tiles_per_side ** 2
     if kind == "mass":
         side = N_PIXEL_MASSPLANE * delta_size_i / MASSPLANE_SIZE * (tile_size / delta_size_i)
@@ -371,7 +371,7 @@ def plane_cost(kind, tiles_per_side, delta_size_i, tile_size):
     else:
         side = N_PIXEL_DELTA * tile_size / delta_size_i
         upload = N_PIXEL_DELTA ** 2 * 4 / 50e9
-    return n * (36e-6 + 2.6e-11 * side * side) + upload
+    return n * (36e-6 + 1.6e-11 * side * side) + upload
 
 
 class _MassCrop:
