@@ -597,6 +597,21 @@ def main():
             del painter
             lc = measure_lightcone(args, 0, 1, local, args.precision)
             extra["lightcone"] = {k: lc[k] for k in LIGHTCONE_FIELDS}
+    if world > 1 and not args.no_extra:
+        # configs[3] at N GPUs: every rank resamples its own 16 tiles 64 times (weak scaling, no exchange); time = max over ranks
+        nv, nd = 16, 64
+        painter.paint_variance(tiles_h[:nv], z=0.0, n_draws=4, seed=1)
+        dist.barrier()
+        t0 = time.perf_counter()
+        mean_v, var_v = painter.paint_variance(tiles_h[:nv], z=0.0, n_draws=nd, seed=1 + rank)
+        tv = torch.tensor([time.perf_counter() - t0, 0.0 if (np.isfinite(mean_v).all() and (var_v >= 0).all()) else 1.0],
+                          dtype=torch.float64, device="cuda")
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            extra["variance"] = {"value": world * nv * nd / float(tv[0]), "unit": "draws/s", "n_gpus": world, "tiles": world * nv,
+                                 "draws_per_tile": nd, "finite": bool(float(tv[1]) == 0.0),
+                                 "note": "host tiles in, mean / variance maps out, every rank its own tiles; parity vs oracle "
+                                         "draws: tests/test_gpu_cvae.py"}
     if world > 1 and not args.no_extra and not args.no_lightcone:
         # configs[4] at N GPUs: ONE line of sight sharded over all ranks (strong scaling; the N = 1 line carries the
         # single-GPU time, map_check must agree between them)

@@ -10,6 +10,7 @@ try:
     d = json.loads(open('gpurun_out/r02_bench_n$N.json').read().strip().splitlines()[-1])
     print({k: d[k] for k in ("value", "ms_per_step", "n_gpus")}, "e2e", d["e2e"]["value"])
     print("lightcone", d.get("lightcone"))
+    print("variance", d.get("variance"))
 except Exception as e:
     print("parse failed", e)
 PY
