@@ -168,8 +168,8 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
-LIGHTCONE_FIELDS = ("metric", "value", "unit", "n_gpus", "scaling", "ms_per_step", "tiles_per_s", "stages_s_max_over_ranks",
-                    "map_check")
+LIGHTCONE_FIELDS = ("metric", "value", "unit", "n_gpus", "scaling", "ms_per_step", "tiles_per_s", "e2e",
+                    "stages_s_max_over_ranks", "map_check")
 
 
 class _ZeroEps:
@@ -254,7 +254,21 @@ def measure_lightcone(args, rank, world, local, precision):
     stages = {}
     ps.paint_lightcone(painter, stage_times=stages, **kw)          # one more pass with per-stage synchronised clocks
     y_fixed = ps.paint_lightcone(_ZeroEps(painter), **kw)          # latents = prior mean: the same map at every N
-    t = torch.tensor([float(np.median(times)), float(np.sum(times))], dtype=torch.float64, device="cuda")
+    # the same line of sight with this rank's planes already resident in HBM (the main metric's `value` convention:
+    # inputs on the device when the timed region starts; the timing above, uploads inside, is its `e2e`)
+    dev_planes = {i: torch.from_numpy(p).to("cuda:%d" % local) for i, p in planes.items()}
+    kw_res = dict(kw, plane_source=lambda i, kind: dev_planes[i])
+    ps.paint_lightcone(painter, **kw_res)
+    times_res = []
+    for _ in range(lc_steps):
+        barrier()
+        t0 = time.perf_counter()
+        ps.paint_lightcone(painter, **kw_res)
+        barrier()
+        times_res.append(time.perf_counter() - t0)
+    y_fixed_res = ps.paint_lightcone(_ZeroEps(painter), **kw_res)
+    del dev_planes
+    t = torch.tensor([float(np.median(times)), float(np.sum(times)), float(np.median(times_res))], dtype=torch.float64, device="cuda")
     st = torch.tensor([stages.get(k, 0.0) for k in ("wait_plane", "extract", "paint", "stitch", "project", "reduce")],
                       dtype=torch.float64, device="cuda")
     if world > 1:
@@ -262,16 +276,27 @@ def measure_lightcone(args, rank, world, local, precision):
         dist.all_reduce(st, op=dist.ReduceOp.MAX)
     if rank != 0:
         return None
-    med = float(t[0])
+    med, med_res = float(t[0]), float(t[2])
     assert y_map is not None and y_map.shape == (1549, 1549) and np.isfinite(y_map).all() and y_map.max() > 0, \
         (np.isfinite(y_map).mean(), float(np.nanmax(y_map)))
+    # planes resident on the device take the device-side crop of the mass planes instead of the host-side one: same map
+    res_err = float(np.sqrt(((y_fixed_res - y_fixed) ** 2).sum() / (y_fixed ** 2).sum()))
+    assert res_err <= 1e-9, res_err
+    # uploaded per line of sight: whole delta planes, of the mass planes only the (expanded) tile crop
+    plane_bytes = int(sum(((ps.N_PIXEL_MASSPLANE * tile_size / ps.MASSPLANE_SIZE if g[0] == "mass" else ps.N_PIXEL_DELTA)
+                           * scale) ** 2 * 4 for g in geom))
     loads = [sum(g[1] ** 2 for g, o in zip(geom, owner) if o == r) for r in range(world)]
     return {
         "metric": "lightcone lines of sight/sec (create_lightcone: %d planes, %d tiles -> 1549^2 y map)" % (n_z, n_tiles),
-        "value": 1.0 / med, "unit": "LOS/s", "n_gpus": world, "steps": lc_steps, "warmup": 1,
-        "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "value": 1.0 / med_res, "unit": "LOS/s", "n_gpus": world, "steps": lc_steps, "warmup": 1,
+        "ms_per_step": 1e3 * med_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"fp16": "f16", "bf16": "bf16"}.get(precision, precision), "data": "synthetic",
-        "tiles_per_s": n_tiles / med,
+        "tiles_per_s": n_tiles / med_res,
+        "e2e": {"value": 1.0 / med, "unit": "LOS/s", "ms_per_step": 1e3 * med, "h2d_bytes_per_step": plane_bytes,
+                "d2h_bytes_per_step": 1549 * 1549 * 8,
+                "api": "process_SLICS.paint_lightcone with page-locked host planes (mass planes: the crop only is "
+                       "uploaded), every plane uploaded inside the timed region, y map read back"},
+        "resident_vs_host_map_rel_l2": res_err,
         "map_check": {"what": "y map painted with eps = 0 (independent of how planes are dealt to ranks): compare "
                               "across n_gpus", "sum": float(y_fixed.sum()), "l2": float(np.sqrt((y_fixed ** 2).sum())),
                       "max": float(y_fixed.max())},
@@ -281,7 +306,8 @@ def measure_lightcone(args, rank, world, local, precision):
                    "parallelism": "whole planes dealt to %d rank(s) by cost (tiles per rank: %s), one NCCL reduce of "
                                   "the 19 MB map" % (world, loads),
                    "timed": "host wall clock between barriers + device synchronisation, max over ranks, median of "
-                            "%d lines of sight; plane uploads (page-locked) inside" % lc_steps},
+                            "%d lines of sight; `value`: planes resident in each rank's HBM, `e2e`: plane uploads "
+                            "(page-locked) inside; the stage split is of the e2e run" % lc_steps},
         "stages_s_max_over_ranks": dict(zip(("wait_plane", "extract", "paint", "stitch", "project", "reduce"),
                                             [float(v) for v in st])),
         "gpu_launches": int(launches), "clocks": clocks}

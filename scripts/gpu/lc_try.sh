@@ -6,5 +6,5 @@ timeout 600 python bench.py --config lightcone --steps 3 --warmup 1 > gpurun_out
 python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/lc_try.json').read().strip().splitlines()[-1])
-print(d["ms_per_step"], d["stages_s_max_over_ranks"], d.get("map_check"))
+print(d["ms_per_step"], d["e2e"]["ms_per_step"], d["resident_vs_host_map_rel_l2"], d["stages_s_max_over_ranks"], d.get("map_check"))
 PY

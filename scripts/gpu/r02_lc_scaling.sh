@@ -11,5 +11,5 @@ for n in (1, 2, 4, 8):
     except Exception as e:
         print(n, "missing", e)
 json.dump(out, open('gpurun_out/r02_lightcone_scaling.json', 'w'), indent=1)
-print([(d["n_gpus"], round(d["ms_per_step"], 1), d.get("map_check", {}).get("sum")) for d in out])
+print([(d["n_gpus"], round(d["ms_per_step"], 1), round(d["e2e"]["ms_per_step"], 1), d.get("map_check", {}).get("sum")) for d in out])
 PY
