@@ -61,6 +61,26 @@ def test_gpu_zoom_accumulate_matches_scipy(order):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("order,side,out", [(5, 1100, 300), (3, 1100, 300), (5, 641, 97)])
+def test_gpu_zoom_accumulate_long_lines_match_scipy(order, side, out):
+    """planes longer than 512 samples take the segment-parallel sweeps (both recursions of every pole fused in shared
+    memory, two poles for the quintic spline create_lightcone asks for): same map as scipy in float64"""
+    import scipy.ndimage
+    import torch
+    from baryon_painter_b200 import _lib
+    dev = torch.device("cuda:0")
+    plane = _field(side, 31).astype(np.float64)
+    plane[7, 9] = np.nan
+    y_ref = 1.75 * scipy.ndimage.zoom(np.where(np.isnan(plane), 0.0, plane), zoom=out / side, order=order, mode="mirror")
+    y_dev = torch.zeros((out, out), dtype=torch.float64, device=dev)
+    d = torch.from_numpy(plane).to(dev)
+    _lib.zoom_accumulate(0, d.data_ptr(), side, out, order, "mirror", 1.75, y_dev.data_ptr(),
+                         torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y_dev.cpu().numpy(), y_ref, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["reflect", "mirror"])
 def test_gpu_zoom_tiles_match_scipy(mode):
     import scipy.ndimage
