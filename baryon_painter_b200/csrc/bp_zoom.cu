@@ -118,8 +118,8 @@ __device__ __forceinline__ int zoom_horizon(double z) { return (int)ceil(-41.446
 // the line ends).  The block loads the window, warp 0 runs, per pole, the causal and then the anticausal recursion of
 // its 32 lines over the whole window in shared memory (exact scipy start / end conditions where the window touches a
 // line end, a zero state elsewhere: what the halo is for) and the block writes the segment.  One read of 1.25-1.5x
-// the data and one write per direction instead of two reads and two writes: the sweeps are bandwidth bound (the crops
-// of a line of sight are 21 GB per float64 pass).  Two blocks per SM: one loads / stores while the other recurses.
+// the data and one write per direction instead of two reads and two writes (the crops of a line of sight are ~20 GB per
+// float64 pass).  Four blocks per SM: some load / store while the others recurse (ncu: 2.4-2.9 TB/s of DRAM traffic).
 constexpr int kSweepThreads = 256;
 constexpr int kSweepSeg = 128;      // 32 lines x (128 + 2 x 32) float64 = 48 KB: four blocks per SM, four recursing warps
 __device__ __forceinline__ void zoom_cp8(double* dst_smem, const double* src) {
